@@ -1,0 +1,678 @@
+// elementwise.cu -- the HBM-bound glue of the hourglass / HRNet hot path on NHWC fp32 tensors:
+// BatchNorm batch statistics (reference: nn.BatchNorm2d in train mode, lib/models/hourglass.py:18-26,117),
+// BN+ReLU apply fused with the tf32 hi/lo operand split, BN backward, 2x2 max-pool fwd/bwd
+// (hourglass.py:82,124), nearest-2x upsample + add (hourglass.py:60,90-91), layout converts, weight
+// re-layout. All kernels are vectorised (float4 along the channel axis = the contiguous NHWC axis) and
+// sized for >= 2 waves of 148 SMs; reductions are deterministic (fixed-order partial buffers, no atomics).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fpd {
+
+namespace {
+
+constexpr int kRedThreads = 256;
+constexpr int kMaxRedBlocks = 1184;  // 8 x 148 SMs
+
+struct RedGeom {
+  int L;       // float4 lanes across channels (C/4)
+  int R;       // pixel rows handled per block iteration
+  int nblocks;
+  int64_t rows_per_block;
+};
+
+inline RedGeom red_geom(int64_t P, int C) {
+  RedGeom g;
+  g.L = C / 4;
+  g.R = kRedThreads / g.L;
+  if (g.R < 1) g.R = 1;
+  int64_t want = (P + (int64_t)g.R * 4 - 1) / ((int64_t)g.R * 4);
+  if (want < 1) want = 1;
+  g.nblocks = (int)(want < kMaxRedBlocks ? want : kMaxRedBlocks);
+  g.rows_per_block = (P + g.nblocks - 1) / g.nblocks;
+  // round rows_per_block up to a multiple of R so chunk boundaries are uniform
+  g.rows_per_block = (g.rows_per_block + g.R - 1) / g.R * g.R;
+  g.nblocks = (int)((P + g.rows_per_block - 1) / g.rows_per_block);
+  return g;
+}
+
+// -------------------------------------------------------------------------------------------------
+// BN statistics: per block -> (n, mean, M2) per channel, merged with Chan's parallel formula in fp64.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRedThreads)
+bn_stats_partial_kernel(const float* __restrict__ x, int64_t P, int C, int L, int R, int64_t rows_per_block,
+                        double* __restrict__ part /*[nblocks][C][2]*/) {
+  extern __shared__ double sm[];  // [R][C][2] (mean, M2) + counts [R]
+  const int tid = threadIdx.x;
+  const int cx = tid % L;
+  const int ry = tid / L;
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t row1 = row0 + rows_per_block;
+  if (row1 > P) row1 = P;
+  float piv[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  int n = 0;
+  if (ry < R) {
+    for (int64_t r = row0 + ry; r < row1; r += R) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C) + cx);
+      const float e[4] = {v.x, v.y, v.z, v.w};
+      if (n == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) piv[j] = e[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d = e[j] - piv[j];
+        s1[j] += d;
+        s2[j] = fmaf(d, d, s2[j]);
+      }
+      ++n;
+    }
+    double* cnt = sm + (size_t)R * C * 2;
+    if (cx == 0) cnt[ry] = (double)n;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double mean = 0.0, m2 = 0.0;
+      if (n > 0) {
+        const double ds1 = (double)s1[j], ds2 = (double)s2[j];
+        mean = (double)piv[j] + ds1 / n;
+        m2 = ds2 - ds1 * ds1 / n;
+        if (m2 < 0.0) m2 = 0.0;
+      }
+      sm[((size_t)ry * C + cx * 4 + j) * 2 + 0] = mean;
+      sm[((size_t)ry * C + cx * 4 + j) * 2 + 1] = m2;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kRedThreads) {
+    const double* cnt = sm + (size_t)R * C * 2;
+    double na = 0.0, ma = 0.0, m2a = 0.0;
+    for (int r = 0; r < R; ++r) {
+      const double nb = cnt[r];
+      if (nb == 0.0) continue;
+      const double mb = sm[((size_t)r * C + c) * 2 + 0];
+      const double m2b = sm[((size_t)r * C + c) * 2 + 1];
+      const double nt = na + nb;
+      const double delta = mb - ma;
+      ma += delta * (nb / nt);
+      m2a += m2b + delta * delta * (na * nb / nt);
+      na = nt;
+    }
+    part[((size_t)blockIdx.x * C + c) * 2 + 0] = ma;
+    part[((size_t)blockIdx.x * C + c) * 2 + 1] = m2a;
+  }
+}
+
+__global__ void bn_stats_final_kernel(const double* __restrict__ part, int nblocks, int64_t rows_per_block,
+                                      int64_t P, int C, float* __restrict__ mean, float* __restrict__ var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double na = 0.0, ma = 0.0, m2a = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    int64_t r0 = (int64_t)b * rows_per_block, r1 = r0 + rows_per_block;
+    if (r1 > P) r1 = P;
+    const double nb = (double)(r1 - r0);
+    if (nb <= 0.0) continue;
+    const double mb = part[((size_t)b * C + c) * 2 + 0];
+    const double m2b = part[((size_t)b * C + c) * 2 + 1];
+    const double nt = na + nb;
+    const double delta = mb - ma;
+    ma += delta * (nb / nt);
+    m2a += m2b + delta * delta * (na * nb / nt);
+    na = nt;
+  }
+  mean[c] = (float)ma;
+  var[c] = (float)(m2a / (double)P);
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ mean, const float* __restrict__ var,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   int64_t count, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ invstd_out, float* __restrict__ rmean,
+                                   float* __restrict__ rvar, float momentum, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float m = mean[c], v = var[c];
+  const float invstd = (float)(1.0 / sqrt((double)v + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = g * invstd;
+  scale[c] = sc;
+  shift[c] = b - m * sc;
+  if (invstd_out) invstd_out[c] = invstd;
+  if (rmean) {
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * m;
+    const float unbiased = count > 1 ? v * ((float)count / (float)(count - 1)) : v;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * unbiased;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// generic per-channel sum reductions (NV sums per element), deterministic two-stage
+// -------------------------------------------------------------------------------------------------
+template <int NV, class F>
+__global__ void __launch_bounds__(kRedThreads)
+channel_reduce_partial_kernel(F f, int64_t P, int C, int L, int R, int64_t rows_per_block,
+                              double* __restrict__ part /*[nblocks][NV][C]*/) {
+  extern __shared__ double sm[];  // [R][NV][C]
+  const int tid = threadIdx.x;
+  const int cx = tid % L;
+  const int ry = tid / L;
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t row1 = row0 + rows_per_block;
+  if (row1 > P) row1 = P;
+  if (ry < R) {
+    double acc[NV][4];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[k][j] = 0.0;
+    float facc[NV][4];
+    int inner = 0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) facc[k][j] = 0.f;
+    for (int64_t r = row0 + ry; r < row1; r += R) {
+      float v[NV][4];
+      f(r, cx, v);
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) facc[k][j] += v[k][j];
+      if (++inner == 16) {  // short fp32 runs, fp64 across runs
+        inner = 0;
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[k][j] += (double)facc[k][j];
+            facc[k][j] = 0.f;
+          }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sm[((size_t)ry * NV + k) * C + cx * 4 + j] = acc[k][j] + (double)facc[k][j];
+  }
+  __syncthreads();
+  for (int i = tid; i < NV * C; i += kRedThreads) {
+    double s = 0.0;
+    for (int r = 0; r < R; ++r) s += sm[(size_t)r * NV * C + i];
+    part[(size_t)blockIdx.x * NV * C + i] = s;
+  }
+}
+
+__global__ void channel_reduce_final_kernel(const double* __restrict__ part, int nblocks, int n /*NV*C*/,
+                                            float scale, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += part[(size_t)b * n + i];
+  out[i] = (float)(s * (double)scale);
+}
+
+struct SumFunctor {
+  const float* dy;
+  int C;
+  __device__ void operator()(int64_t r, int cx, float (&v)[1][4]) const {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(dy + r * C) + cx);
+    v[0][0] = a.x; v[0][1] = a.y; v[0][2] = a.z; v[0][3] = a.w;
+  }
+};
+
+struct BnBwdFunctor {
+  const float* da; const float* x; const float* mean; const float* invstd; const float* scale; const float* shift;
+  int relu; int C;
+  __device__ void operator()(int64_t r, int cx, float (&v)[2][4]) const {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(da + r * C) + cx);
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + r * C) + cx);
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + cx);
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + cx);
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cx);
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cx);
+    const float ge[4] = {g.x, g.y, g.z, g.w}, xe[4] = {xv.x, xv.y, xv.z, xv.w}, me[4] = {m.x, m.y, m.z, m.w},
+                ie[4] = {is.x, is.y, is.z, is.w}, se[4] = {sc.x, sc.y, sc.z, sc.w}, he[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool on = !relu || (fmaf(xe[j], se[j], he[j]) > 0.f);
+      const float dz = on ? ge[j] : 0.f;
+      v[0][j] = dz;
+      v[1][j] = dz * ((xe[j] - me[j]) * ie[j]);
+    }
+  }
+};
+
+// -------------------------------------------------------------------------------------------------
+// pointwise kernels
+// -------------------------------------------------------------------------------------------------
+__global__ void affine_act_split_kernel(const float4* __restrict__ x, const float* __restrict__ scale,
+                                        const float* __restrict__ shift, int relu, float4* __restrict__ hi,
+                                        float4* __restrict__ lo, int64_t n4, int L) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = __ldg(x + i);
+    if (scale) {
+      const int cx = (int)(i % L);
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cx);
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cx);
+      v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+      v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    }
+    if (relu) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    }
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
+    split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(const float4* __restrict__ da, const float4* __restrict__ x,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ gamma, int relu, const float* __restrict__ sums,
+                                    int accumulate, float4* __restrict__ dx, int64_t n4, int L, float inv_count) {
+  const int C = L * 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % L);
+    const float4 g = __ldg(da + i);
+    const float4 xv = __ldg(x + i);
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + cx);
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + cx);
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cx);
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cx);
+    const float4 gm = gamma ? __ldg(reinterpret_cast<const float4*>(gamma) + cx) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sums) + cx);
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(sums + C) + cx);
+    const float ge[4] = {g.x, g.y, g.z, g.w}, xe[4] = {xv.x, xv.y, xv.z, xv.w}, me[4] = {m.x, m.y, m.z, m.w},
+                ie[4] = {is.x, is.y, is.z, is.w}, se[4] = {sc.x, sc.y, sc.z, sc.w}, he[4] = {sh.x, sh.y, sh.z, sh.w},
+                ga[4] = {gm.x, gm.y, gm.z, gm.w}, a0[4] = {s0.x, s0.y, s0.z, s0.w}, a1[4] = {s1.x, s1.y, s1.z, s1.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool on = !relu || (fmaf(xe[j], se[j], he[j]) > 0.f);
+      const float dz = on ? ge[j] : 0.f;
+      const float xh = (xe[j] - me[j]) * ie[j];
+      o[j] = ga[j] * ie[j] * (dz - a0[j] * inv_count - xh * a1[j] * inv_count);
+    }
+    float4 r = make_float4(o[0], o[1], o[2], o[3]);
+    if (accumulate) {
+      const float4 p = dx[i];
+      r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w;
+    }
+    dx[i] = r;
+  }
+}
+
+__global__ void affine_act_bwd_kernel(const float4* __restrict__ da, const float4* __restrict__ x,
+                                      const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                                      int accumulate, float4* __restrict__ dx, int64_t n4, int L) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % L);
+    const float4 g = __ldg(da + i);
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (scale) {
+      sc = __ldg(reinterpret_cast<const float4*>(scale) + cx);
+      sh = __ldg(reinterpret_cast<const float4*>(shift) + cx);
+    }
+    float4 r = make_float4(g.x * sc.x, g.y * sc.y, g.z * sc.z, g.w * sc.w);
+    if (relu) {
+      const float4 xv = __ldg(x + i);
+      if (!(fmaf(xv.x, sc.x, sh.x) > 0.f)) r.x = 0.f;
+      if (!(fmaf(xv.y, sc.y, sh.y) > 0.f)) r.y = 0.f;
+      if (!(fmaf(xv.z, sc.z, sh.z) > 0.f)) r.z = 0.f;
+      if (!(fmaf(xv.w, sc.w, sh.w) > 0.f)) r.w = 0.f;
+    }
+    if (accumulate) {
+      const float4 p = dx[i];
+      r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w;
+    }
+    dx[i] = r;
+  }
+}
+
+__global__ void maxpool2x2_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int B, int Ho, int Wo,
+                                      int L) {
+  const int64_t n = (int64_t)B * Ho * Wo * L;
+  const int W = Wo * 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % L);
+    int64_t t = i / L;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const int64_t base = (((int64_t)b * Ho * 2 + ho * 2) * W + wo * 2) * L + cx;
+    const float4 a = __ldg(x + base), bb = __ldg(x + base + L), c = __ldg(x + base + (int64_t)W * L),
+                 d = __ldg(x + base + (int64_t)W * L + L);
+    float4 r;
+    r.x = fmaxf(fmaxf(a.x, bb.x), fmaxf(c.x, d.x));
+    r.y = fmaxf(fmaxf(a.y, bb.y), fmaxf(c.y, d.y));
+    r.z = fmaxf(fmaxf(a.z, bb.z), fmaxf(c.z, d.z));
+    r.w = fmaxf(fmaxf(a.w, bb.w), fmaxf(c.w, d.w));
+    y[i] = r;
+  }
+}
+
+// gradient goes to the first maximum in window scan order (row-major), like ATen's max_pool2d backward
+__device__ __forceinline__ void pool_route(float a, float b, float c, float d, float g, float& oa, float& ob,
+                                           float& oc, float& od) {
+  int k = 0;
+  float m = a;
+  if (b > m) { m = b; k = 1; }
+  if (c > m) { m = c; k = 2; }
+  if (d > m) { m = d; k = 3; }
+  oa = k == 0 ? g : 0.f; ob = k == 1 ? g : 0.f; oc = k == 2 ? g : 0.f; od = k == 3 ? g : 0.f;
+}
+
+__global__ void maxpool2x2_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ dy,
+                                      float4* __restrict__ dx, int accumulate, int B, int Ho, int Wo, int L) {
+  const int64_t n = (int64_t)B * Ho * Wo * L;
+  const int W = Wo * 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % L);
+    int64_t t = i / L;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const int64_t base = (((int64_t)b * Ho * 2 + ho * 2) * W + wo * 2) * L + cx;
+    const int64_t i00 = base, i01 = base + L, i10 = base + (int64_t)W * L, i11 = i10 + L;
+    const float4 a = __ldg(x + i00), bb = __ldg(x + i01), c = __ldg(x + i10), d = __ldg(x + i11);
+    const float4 g = __ldg(dy + i);
+    float4 ra, rb, rc, rd;
+    pool_route(a.x, bb.x, c.x, d.x, g.x, ra.x, rb.x, rc.x, rd.x);
+    pool_route(a.y, bb.y, c.y, d.y, g.y, ra.y, rb.y, rc.y, rd.y);
+    pool_route(a.z, bb.z, c.z, d.z, g.z, ra.z, rb.z, rc.z, rd.z);
+    pool_route(a.w, bb.w, c.w, d.w, g.w, ra.w, rb.w, rc.w, rd.w);
+    if (accumulate) {
+      float4 p;
+      p = dx[i00]; ra.x += p.x; ra.y += p.y; ra.z += p.z; ra.w += p.w;
+      p = dx[i01]; rb.x += p.x; rb.y += p.y; rb.z += p.z; rb.w += p.w;
+      p = dx[i10]; rc.x += p.x; rc.y += p.y; rc.z += p.z; rc.w += p.w;
+      p = dx[i11]; rd.x += p.x; rd.y += p.y; rd.z += p.z; rd.w += p.w;
+    }
+    dx[i00] = ra; dx[i01] = rb; dx[i10] = rc; dx[i11] = rd;
+  }
+}
+
+__global__ void upsample2x_add_kernel(const float4* __restrict__ up1, const float4* __restrict__ low,
+                                      float4* __restrict__ out, int B, int H, int W, int L) {
+  const int64_t n = (int64_t)B * H * W * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % L);
+    int64_t t = i / L;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int b = (int)(t / H);
+    const float4 a = __ldg(up1 + i);
+    const float4 l = __ldg(low + (((int64_t)b * (H / 2) + h / 2) * (W / 2) + w / 2) * L + cx);
+    out[i] = make_float4(a.x + l.x, a.y + l.y, a.z + l.z, a.w + l.w);
+  }
+}
+
+__global__ void upsample2x_bwd_kernel(const float4* __restrict__ dout, float4* __restrict__ dlow, int B, int Ho,
+                                      int Wo, int L) {  // Ho,Wo = low-res size
+  const int64_t n = (int64_t)B * Ho * Wo * L;
+  const int W = Wo * 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % L);
+    int64_t t = i / L;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const int64_t base = (((int64_t)b * Ho * 2 + ho * 2) * W + wo * 2) * L + cx;
+    const float4 a = __ldg(dout + base), bb = __ldg(dout + base + L), c = __ldg(dout + base + (int64_t)W * L),
+                 d = __ldg(dout + base + (int64_t)W * L + L);
+    dlow[i] = make_float4((a.x + bb.x) + (c.x + d.x), (a.y + bb.y) + (c.y + d.y), (a.z + bb.z) + (c.z + d.z),
+                          (a.w + bb.w) + (c.w + d.w));
+  }
+}
+
+// NCHW <-> NHWC through a 32x33 shared-memory transpose tile (coalesced on both sides)
+__global__ void transpose_cs_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  // in: [batch][rows][cols] -> out: [batch][cols][rows]
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const float* src = in + (size_t)b * rows * cols;
+  float* dst = out + (size_t)b * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[(size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+__global__ void add_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ o,
+                           int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 x = __ldg(a + i), y = __ldg(b + i);
+    o[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+  }
+}
+
+__global__ void weight_prep_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo,
+                                   int O, int I, int k, int for_dgrad) {
+  const int taps = k * k;
+  const int64_t n = (int64_t)O * I * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // destination index i -> (tap, row, col)
+    int64_t t = i;
+    int col, row, tap;
+    if (!for_dgrad) {  // [tap][O][I]
+      col = (int)(t % I); t /= I; row = (int)(t % O); tap = (int)(t / O);
+      const float v = w[((size_t)row * I + col) * taps + tap];
+      float h, l; split_tf32(v, h, l);
+      hi[i] = h; if (lo) lo[i] = l;
+    } else {  // [tap'][I][O] with tap' = taps-1-tap (180-degree flip)
+      col = (int)(t % O); t /= O; row = (int)(t % I); tap = (int)(t / I);
+      const float v = w[((size_t)col * I + row) * taps + (taps - 1 - tap)];
+      float h, l; split_tf32(v, h, l);
+      hi[i] = h; if (lo) lo[i] = l;
+    }
+  }
+}
+
+inline int grid_for(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = 148 * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+// =================================================================================================
+// launchers
+// =================================================================================================
+size_t bn_stats_workspace_bytes(int64_t P, int C) {
+  RedGeom g = red_geom(P, C);
+  return (size_t)g.nblocks * C * 2 * sizeof(double);
+}
+
+int bn_stats(const float* x, int64_t P, int C, float* mean, float* var_biased, void* workspace, size_t ws_bytes,
+             cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "bn_stats: C=%d must be a multiple of 4 in [4,1024]", C);
+  FPD_REQUIRE(P > 0, "bn_stats: empty tensor");
+  RedGeom g = red_geom(P, C);
+  FPD_REQUIRE(ws_bytes >= (size_t)g.nblocks * C * 2 * sizeof(double), "bn_stats: workspace too small");
+  const size_t smem = ((size_t)g.R * C * 2 + g.R) * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(bn_stats_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        160 * 1024));
+    attr = true;
+  }
+  bn_stats_partial_kernel<<<g.nblocks, kRedThreads, smem, stream>>>(x, P, C, g.L, g.R, g.rows_per_block,
+                                                                    (double*)workspace);
+  FPD_LAUNCH_CHECK();
+  bn_stats_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>((const double*)workspace, g.nblocks,
+                                                             g.rows_per_block, P, C, mean, var_biased);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int bn_finalize(const float* mean, const float* var_biased, const float* gamma, const float* beta, float eps,
+                int64_t count, float* scale, float* shift, float* invstd, float* running_mean, float* running_var,
+                float momentum, int C, cudaStream_t stream) {
+  FPD_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats must come in pairs");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(mean, var_biased, gamma, beta, eps, count, scale, shift,
+                                                          invstd, running_mean, running_var, momentum, C);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int affine_act_split(const float* x, const float* scale, const float* shift, int relu, float* a_hi, float* a_lo,
+                     int64_t P, int C, cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0, "affine_act_split: C=%d must be a multiple of 4", C);
+  FPD_REQUIRE((scale == nullptr) == (shift == nullptr), "affine_act_split: scale/shift must come in pairs");
+  const int64_t n4 = P * C / 4;
+  affine_act_split_kernel<<<grid_for(n4, 256), 256, 0, stream>>>((const float4*)x, scale, shift, relu, (float4*)a_hi,
+                                                                 (float4*)a_lo, n4, C / 4);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int maxpool2x2_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2x2: bad shape H=%d W=%d C=%d", H, W, C);
+  const int64_t n = (int64_t)B * (H / 2) * (W / 2) * (C / 4);
+  maxpool2x2_fwd_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const float4*)x, (float4*)y, B, H / 2, W / 2, C / 4);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int maxpool2x2_bwd(const float* x, const float* dy, float* dx, int accumulate, int B, int H, int W, int C,
+                   cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2x2_bwd: bad shape H=%d W=%d C=%d", H, W, C);
+  const int64_t n = (int64_t)B * (H / 2) * (W / 2) * (C / 4);
+  maxpool2x2_bwd_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const float4*)x, (const float4*)dy, (float4*)dx,
+                                                              accumulate, B, H / 2, W / 2, C / 4);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int upsample2x_add(const float* up1, const float* low, float* out, int B, int H, int W, int C, cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "upsample2x_add: bad shape H=%d W=%d C=%d", H, W, C);
+  const int64_t n = (int64_t)B * H * W * (C / 4);
+  upsample2x_add_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const float4*)up1, (const float4*)low, (float4*)out,
+                                                              B, H, W, C / 4);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int upsample2x_bwd(const float* dout, float* dlow, int B, int H, int W, int C, cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "upsample2x_bwd: bad shape H=%d W=%d C=%d", H, W, C);
+  const int64_t n = (int64_t)B * (H / 2) * (W / 2) * (C / 4);
+  upsample2x_bwd_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const float4*)dout, (float4*)dlow, B, H / 2, W / 2,
+                                                              C / 4);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream) {
+  // per image: [C][HW] -> [HW][C]
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  transpose_cs_kernel<<<grid, block, 0, stream>>>(x, y, C, H * W);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream) {
+  dim3 grid((C + 31) / 32, (H * W + 31) / 32, B), block(32, 8);
+  transpose_cs_kernel<<<grid, block, 0, stream>>>(x, y, H * W, C);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int add_tensors(const float* a, const float* b, float* out, int64_t n, cudaStream_t stream) {
+  FPD_REQUIRE(n % 4 == 0, "add_tensors: n must be a multiple of 4");
+  add_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>((const float4*)a, (const float4*)b, (float4*)out, n / 4);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+size_t channel_reduce_workspace_bytes(int64_t P, int C) {
+  RedGeom g = red_geom(P, C);
+  return (size_t)g.nblocks * 2 * C * sizeof(double);
+}
+
+template <int NV, class F>
+static int run_channel_reduce(F f, int64_t P, int C, float scale, float* out, void* workspace, size_t ws_bytes,
+                              cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "channel reduce: C=%d must be a multiple of 4 in [4,1024]", C);
+  RedGeom g = red_geom(P, C);
+  FPD_REQUIRE(ws_bytes >= (size_t)g.nblocks * NV * C * sizeof(double), "channel reduce: workspace too small");
+  const size_t smem = (size_t)g.R * NV * C * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(channel_reduce_partial_kernel<NV, F>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
+  channel_reduce_partial_kernel<NV, F><<<g.nblocks, kRedThreads, smem, stream>>>(f, P, C, g.L, g.R,
+                                                                                  g.rows_per_block,
+                                                                                  (double*)workspace);
+  FPD_LAUNCH_CHECK();
+  channel_reduce_final_kernel<<<(NV * C + 127) / 128, 128, 0, stream>>>((const double*)workspace, g.nblocks, NV * C,
+                                                                        scale, out);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int channel_sum(const float* dy, int64_t P, int C, float scale, float* out, void* workspace, size_t ws_bytes,
+                cudaStream_t stream) {
+  SumFunctor f{dy, C};
+  return run_channel_reduce<1>(f, P, C, scale, out, workspace, ws_bytes, stream);
+}
+
+int bn_bwd_reduce(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
+                  const float* shift, int relu, int64_t P, int C, float* sums, void* workspace, size_t ws_bytes,
+                  cudaStream_t stream) {
+  BnBwdFunctor f{da, x, mean, invstd, scale, shift, relu, C};
+  return run_channel_reduce<2>(f, P, C, 1.f, sums, workspace, ws_bytes, stream);
+}
+
+int bn_bwd_apply(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
+                 const float* shift, const float* gamma, int relu, const float* sums, int accumulate, float* dx,
+                 int64_t P, int C, cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0, "bn_bwd_apply: C=%d must be a multiple of 4", C);
+  const int64_t n4 = P * C / 4;
+  bn_bwd_apply_kernel<<<grid_for(n4, 256), 256, 0, stream>>>((const float4*)da, (const float4*)x, mean, invstd,
+                                                             scale, shift, gamma, relu, sums, accumulate,
+                                                             (float4*)dx, n4, C / 4, 1.f / (float)P);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int affine_act_bwd(const float* da, const float* x, const float* scale, const float* shift, int relu,
+                   int accumulate, float* dx, int64_t P, int C, cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0, "affine_act_bwd: C=%d must be a multiple of 4", C);
+  const int64_t n4 = P * C / 4;
+  affine_act_bwd_kernel<<<grid_for(n4, 256), 256, 0, stream>>>((const float4*)da, (const float4*)x, scale, shift,
+                                                               relu, accumulate, (float4*)dx, n4, C / 4);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int weight_prep(const float* w_oihw, float* w_hi, float* w_lo, int O, int I, int k, int for_dgrad,
+                cudaStream_t stream) {
+  const int64_t n = (int64_t)O * I * k * k;
+  weight_prep_kernel<<<grid_for(n, 256), 256, 0, stream>>>(w_oihw, w_hi, w_lo, O, I, k, for_dgrad);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int device_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace fpd

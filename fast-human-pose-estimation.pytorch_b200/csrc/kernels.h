@@ -1,0 +1,102 @@
+// kernels.h -- internal launcher declarations (C++), one per kernel family. The public C ABI that
+// wraps these lives in api.cu / include/fpd_b200.h. Every launcher: launches only on `stream`, never
+// allocates or frees device memory, never synchronises, returns FPD_OK or a negative error code.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fpd {
+
+// ---- conv_tc.cu : tcgen05 implicit GEMM (1x1 / 3x3 stride 1) ----
+bool conv_tc_supported(int Cin, int Cout, int ksize);
+int conv_tc_launch(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, const float* bias,
+                   const float* residual, const float* relu_mask, float* y, float out_scale, int B, int H, int W,
+                   int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream);
+
+// ---- wgrad_tc.cu : tcgen05 weight-gradient GEMM (K = pixels) ----
+bool wgrad_tc_supported(int Cin, int Cout, int ksize);
+size_t wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize, int num_sms);
+int wgrad_tc_launch(const float* a_hi, const float* a_lo, const float* dy_hi, const float* dy_lo, float* dw_oihw,
+                    float scale, int B, int H, int W, int Cin, int Cout, int ksize, void* workspace,
+                    size_t workspace_bytes, int num_sms, cudaStream_t stream);
+
+// ---- conv_simt.cu : generic fp32 CUDA-core convolution (any k / stride / pad, NHWC activations,
+//      OIHW weights). Used for the shapes the tensor-core kernels do not take (7x7 stem, 16-channel
+//      score convs) and as the on-device cross-check in tests. ----
+int conv_simt_fwd(const float* x, const float* w_oihw, const float* bias, const float* residual, float* y, int B,
+                  int H, int W, int Cin, int Cout, int k, int stride, int pad, cudaStream_t stream);
+int conv_simt_dgrad(const float* dy, const float* w_oihw, float* dx, int B, int H, int W, int Cin, int Cout, int k,
+                    int stride, int pad, cudaStream_t stream);  // H,W = input size; dx[B,H,W,Cin]
+int conv_simt_wgrad(const float* x, const float* dy, float* dw_oihw, float scale, int B, int H, int W, int Cin,
+                    int Cout, int k, int stride, int pad, cudaStream_t stream);
+
+// ---- elementwise.cu ----
+// Per-channel batch statistics of x[P,C] (numerically robust: per-chunk shifted sums, Chan merge in fp64).
+size_t bn_stats_workspace_bytes(int64_t P, int C);
+int bn_stats(const float* x, int64_t P, int C, float* mean, float* var_biased, void* workspace, size_t ws_bytes,
+             cudaStream_t stream);
+// scale = gamma*rsqrt(var+eps), shift = beta - mean*scale ; optional running-stat update (momentum, unbiased var)
+int bn_finalize(const float* mean, const float* var_biased, const float* gamma, const float* beta, float eps,
+                int64_t count, float* scale, float* shift, float* invstd, float* running_mean, float* running_var,
+                float momentum, int C, cudaStream_t stream);
+// a = act(x*scale+shift) (scale/shift may be null = identity; relu optional); hi = tf32(a), lo = tf32(a-hi)
+int affine_act_split(const float* x, const float* scale, const float* shift, int relu, float* a_hi, float* a_lo,
+                     int64_t P, int C, cudaStream_t stream);
+int maxpool2x2_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream);
+int maxpool2x2_bwd(const float* x, const float* dy, float* dx, int accumulate, int B, int H, int W, int C,
+                   cudaStream_t stream);
+int upsample2x_add(const float* up1, const float* low, float* out, int B, int H, int W, int C,
+                   cudaStream_t stream);  // H,W = output size
+int upsample2x_bwd(const float* dout, float* dlow, int B, int H, int W, int C, cudaStream_t stream);
+int nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream);
+int nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream);
+int add_tensors(const float* a, const float* b, float* out, int64_t n, cudaStream_t stream);  // out = a + b
+size_t channel_reduce_workspace_bytes(int64_t P, int C);
+// sum over pixels of dy[P,C] -> out[C] (out = scale*sum)
+int channel_sum(const float* dy, int64_t P, int C, float scale, float* out, void* workspace, size_t ws_bytes,
+                cudaStream_t stream);
+// BN(+ReLU) backward, phase 1: dz = da * (relu ? (x*scale+shift > 0) : 1); sums[0:C] = sum dz,
+// sums[C:2C] = sum dz * xhat  where xhat = (x-mean)*invstd.
+int bn_bwd_reduce(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
+                  const float* shift, int relu, int64_t P, int C, float* sums, void* workspace, size_t ws_bytes,
+                  cudaStream_t stream);
+// phase 2: dx (=|+=) gamma*invstd*(dz - sum_dz/P - xhat*sum_dzx/P); also writes dgamma = sum_dzx, dbeta = sum_dz
+int bn_bwd_apply(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
+                 const float* shift, const float* gamma, int relu, const float* sums, int accumulate, float* dx,
+                 int64_t P, int C, cudaStream_t stream);
+// eval-mode / no-stat variant: dx (=|+=) da * mask * scale
+int affine_act_bwd(const float* da, const float* x, const float* scale, const float* shift, int relu,
+                   int accumulate, float* dx, int64_t P, int C, cudaStream_t stream);
+// OIHW fp32 -> [tap][O][I] (fwd) or [flipped tap][I][O] (dgrad), split into tf32 hi/lo
+int weight_prep(const float* w_oihw, float* w_hi, float* w_lo, int O, int I, int k, int for_dgrad,
+                cudaStream_t stream);
+
+// ---- loss.cu : fused FPD loss + gradient ----
+// out_s: S pointers to NHWC [B,h,w,J] student heat-maps; target NCHW [B,J,h,w]; teacher NHWC [B,h,w,J] or null;
+// tw [B,J]; losses[3] = {pose, kd, total}; grads: S pointers (NHWC) or null.
+size_t fpd_loss_workspace_bytes(int B, int J, int h, int w);
+int fpd_loss(const float* const* outs_dev_ptrs_host, int S, const float* target_nchw, const float* teacher_nhwc,
+             const float* tw, float alpha, float* const* grads_host, float grad_scale, float* losses, int B, int J,
+             int h, int w, void* workspace, size_t ws_bytes, cudaStream_t stream);
+// reference-compatible single JointsMSELoss on NCHW tensors (lib/core/loss.py:21-39)
+int joints_mse(const float* out_nchw, const float* target_nchw, const float* tw, float* loss, float* grad_out,
+               float grad_scale_unused, int B, int J, int hw, void* workspace, size_t ws_bytes, cudaStream_t stream);
+
+// ---- decode.cu ----
+// flip-test merge + arg-max: hm/hm_flip NHWC [B,h,w,J]; out avg NCHW (optional), idx[B,J] int32, maxval[B,J]
+int flip_merge_argmax(const float* hm, const float* hm_flip, const int* flip_perm, int shift, float* avg_nchw,
+                      int* idx, float* maxval, int B, int J, int h, int w, cudaStream_t stream);
+int argmax_nchw(const float* hm, int* idx, float* maxval, int BJ, int hw, cudaStream_t stream);
+
+// ---- nms.cu ----
+size_t nms_workspace_bytes(int n);
+int nms_device(const float* boxes_sorted_dev, int n, int box_dim, float thresh, int* keep_dev, int* num_keep_dev,
+               void* workspace, size_t ws_bytes, cudaStream_t stream);
+
+// ---- adam.cu ----
+int adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+              float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream);
+
+int device_sm_count();
+
+}  // namespace fpd

@@ -1,0 +1,294 @@
+"""Tensor-level wrappers over the C ABI: torch is used only for device memory and streams.
+
+Every function takes contiguous fp32 CUDA tensors, enqueues on torch's current stream and returns
+(or fills) tensors. Activations are NHWC ([B,H,W,C]) unless a name says otherwise.
+"""
+import ctypes
+
+import torch
+
+from . import _native as N
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, name):
+    if t is None:
+        return
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise ValueError("%s must be a contiguous fp32 CUDA tensor (got %s %s %s)" % (name, t.device, t.dtype,
+                                                                                 t.is_contiguous()))
+
+
+class Workspace:
+    """Grow-only scratch buffer handed to the kernels that need one (no allocation at call time once warm)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        nbytes = int(nbytes)
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+_ws = Workspace()
+
+
+def conv2d_tc_supported(cin, cout, k):
+    return bool(N.lib().fpd_conv2d_tc_supported(cin, cout, k))
+
+
+def weight_prep(w_oihw, for_dgrad=False, split=True):
+    _chk(w_oihw, "w")
+    O, I, k, _ = w_oihw.shape
+    shape = (k * k, I, O) if for_dgrad else (k * k, O, I)
+    hi = torch.empty(shape, dtype=torch.float32, device=w_oihw.device)
+    lo = torch.empty_like(hi) if split else None
+    N.check(N.lib().fpd_weight_prep(_p(w_oihw), _p(hi), _p(lo), O, I, k, int(for_dgrad), _stream()), "weight_prep")
+    return hi, lo
+
+
+def affine_act_split(x, scale=None, shift=None, relu=False, split=True, out_hi=None, out_lo=None):
+    _chk(x, "x")
+    C = x.shape[-1]
+    P = x.numel() // C
+    hi = out_hi if out_hi is not None else torch.empty_like(x)
+    lo = (out_lo if out_lo is not None else torch.empty_like(x)) if split else None
+    N.check(N.lib().fpd_affine_act_split(_p(x), _p(scale), _p(shift), int(relu), _p(hi), _p(lo), P, C, _stream()),
+            "affine_act_split")
+    return hi, lo
+
+
+def conv2d_tc(a_hi, a_lo, w_hi, w_lo, ksize, bias=None, residual=None, relu_mask=None, out=None, out_scale=1.0):
+    B, H, W, Cin = a_hi.shape
+    Cout = w_hi.shape[1]
+    y = out if out is not None else torch.empty((B, H, W, Cout), dtype=torch.float32, device=a_hi.device)
+    N.check(N.lib().fpd_conv2d_tc(_p(a_hi), _p(a_lo), _p(w_hi), _p(w_lo), _p(bias), _p(residual), _p(relu_mask), _p(y),
+                                  float(out_scale), B, H, W, Cin, Cout, ksize, _stream()), "conv2d_tc")
+    return y
+
+
+def conv2d_simt_fwd(x, w_oihw, bias=None, residual=None, stride=1, pad=0, out=None):
+    B, H, W, Cin = x.shape
+    Cout, _, k, _ = w_oihw.shape
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    y = out if out is not None else torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+    N.check(N.lib().fpd_conv2d_simt_fwd(_p(x), _p(w_oihw), _p(bias), _p(residual), _p(y), B, H, W, Cin, Cout, k, stride,
+                                        pad, _stream()), "conv2d_simt_fwd")
+    return y
+
+
+def conv2d_simt_dgrad(dy, w_oihw, in_hw, stride=1, pad=0, out=None):
+    B = dy.shape[0]
+    H, W = in_hw
+    Cout, Cin, k, _ = w_oihw.shape
+    dx = out if out is not None else torch.empty((B, H, W, Cin), dtype=torch.float32, device=dy.device)
+    N.check(N.lib().fpd_conv2d_simt_dgrad(_p(dy), _p(w_oihw), _p(dx), B, H, W, Cin, Cout, k, stride, pad, _stream()),
+            "conv2d_simt_dgrad")
+    return dx
+
+
+def conv2d_simt_wgrad(x, dy, k, stride=1, pad=0, scale=1.0, out=None):
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    dw = out if out is not None else torch.empty((Cout, Cin, k, k), dtype=torch.float32, device=x.device)
+    N.check(N.lib().fpd_conv2d_simt_wgrad(_p(x), _p(dy), _p(dw), float(scale), B, H, W, Cin, Cout, k, stride, pad,
+                                          _stream()), "conv2d_simt_wgrad")
+    return dw
+
+
+def conv2d_wgrad_tc_supported(cin, cout, k):
+    return bool(N.lib().fpd_conv2d_wgrad_tc_supported(cin, cout, k))
+
+
+def conv2d_wgrad_tc(a_hi, a_lo, dy_hi, dy_lo, ksize, scale=1.0, out=None):
+    B, H, W, Cin = a_hi.shape
+    Cout = dy_hi.shape[-1]
+    dw = out if out is not None else torch.empty((Cout, Cin, ksize, ksize), dtype=torch.float32, device=a_hi.device)
+    nb = N.lib().fpd_conv2d_wgrad_tc_workspace_bytes(B, H, W, Cin, Cout, ksize)
+    ws = _ws.get(nb, a_hi.device)
+    N.check(N.lib().fpd_conv2d_wgrad_tc(_p(a_hi), _p(a_lo), _p(dy_hi), _p(dy_lo), _p(dw), float(scale), B, H, W, Cin,
+                                        Cout, ksize, _p(ws), ws.numel(), _stream()), "conv2d_wgrad_tc")
+    return dw
+
+
+def bn_stats(x):
+    C = x.shape[-1]
+    P = x.numel() // C
+    mean = torch.empty(C, dtype=torch.float32, device=x.device)
+    var = torch.empty_like(mean)
+    ws = _ws.get(N.lib().fpd_bn_stats_workspace_bytes(P, C), x.device)
+    N.check(N.lib().fpd_bn_stats(_p(x), P, C, _p(mean), _p(var), _p(ws), ws.numel(), _stream()), "bn_stats")
+    return mean, var
+
+
+def bn_finalize(mean, var, gamma, beta, eps, count, running_mean=None, running_var=None, momentum=0.1):
+    C = mean.numel()
+    scale = torch.empty_like(mean)
+    shift = torch.empty_like(mean)
+    invstd = torch.empty_like(mean)
+    N.check(N.lib().fpd_bn_finalize(_p(mean), _p(var), _p(gamma), _p(beta), float(eps), int(count), _p(scale),
+                                    _p(shift), _p(invstd), _p(running_mean), _p(running_var), float(momentum), C,
+                                    _stream()), "bn_finalize")
+    return scale, shift, invstd
+
+
+def channel_sum(dy, scale=1.0):
+    C = dy.shape[-1]
+    P = dy.numel() // C
+    out = torch.empty(C, dtype=torch.float32, device=dy.device)
+    ws = _ws.get(N.lib().fpd_channel_reduce_workspace_bytes(P, C), dy.device)
+    N.check(N.lib().fpd_channel_sum(_p(dy), P, C, float(scale), _p(out), _p(ws), ws.numel(), _stream()), "channel_sum")
+    return out
+
+
+def bn_bwd(da, x, mean, invstd, scale, shift, gamma, relu, accumulate_into=None):
+    """Returns (dx, dgamma, dbeta) for y = relu?(bn(x)) given da = dL/dy."""
+    C = x.shape[-1]
+    P = x.numel() // C
+    sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+    ws = _ws.get(N.lib().fpd_channel_reduce_workspace_bytes(P, C), x.device)
+    N.check(N.lib().fpd_bn_bwd_reduce(_p(da), _p(x), _p(mean), _p(invstd), _p(scale), _p(shift), int(relu), P, C,
+                                      _p(sums), _p(ws), ws.numel(), _stream()), "bn_bwd_reduce")
+    dx = accumulate_into if accumulate_into is not None else torch.empty_like(x)
+    N.check(N.lib().fpd_bn_bwd_apply(_p(da), _p(x), _p(mean), _p(invstd), _p(scale), _p(shift), _p(gamma), int(relu),
+                                     _p(sums), int(accumulate_into is not None), _p(dx), P, C, _stream()),
+            "bn_bwd_apply")
+    return dx, sums[C:], sums[:C]
+
+
+def affine_act_bwd(da, x, scale, shift, relu, accumulate_into=None):
+    C = x.shape[-1]
+    P = x.numel() // C
+    dx = accumulate_into if accumulate_into is not None else torch.empty_like(x)
+    N.check(N.lib().fpd_affine_act_bwd(_p(da), _p(x), _p(scale), _p(shift), int(relu),
+                                       int(accumulate_into is not None), _p(dx), P, C, _stream()), "affine_act_bwd")
+    return dx
+
+
+def maxpool2x2(x, out=None):
+    B, H, W, C = x.shape
+    y = out if out is not None else torch.empty((B, H // 2, W // 2, C), dtype=torch.float32, device=x.device)
+    N.check(N.lib().fpd_maxpool2x2_fwd(_p(x), _p(y), B, H, W, C, _stream()), "maxpool2x2_fwd")
+    return y
+
+
+def maxpool2x2_bwd(x, dy, accumulate_into=None):
+    B, H, W, C = x.shape
+    dx = accumulate_into if accumulate_into is not None else torch.empty_like(x)
+    N.check(N.lib().fpd_maxpool2x2_bwd(_p(x), _p(dy), _p(dx), int(accumulate_into is not None), B, H, W, C, _stream()),
+            "maxpool2x2_bwd")
+    return dx
+
+
+def upsample2x_add(up1, low, out=None):
+    B, H, W, C = up1.shape
+    y = out if out is not None else torch.empty_like(up1)
+    N.check(N.lib().fpd_upsample2x_add(_p(up1), _p(low), _p(y), B, H, W, C, _stream()), "upsample2x_add")
+    return y
+
+
+def upsample2x_bwd(dout, out=None):
+    B, H, W, C = dout.shape
+    d = out if out is not None else torch.empty((B, H // 2, W // 2, C), dtype=torch.float32, device=dout.device)
+    N.check(N.lib().fpd_upsample2x_bwd(_p(dout), _p(d), B, H, W, C, _stream()), "upsample2x_bwd")
+    return d
+
+
+def nchw_to_nhwc(x, out=None):
+    B, C, H, W = x.shape
+    y = out if out is not None else torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
+    N.check(N.lib().fpd_nchw_to_nhwc(_p(x), _p(y), B, C, H, W, _stream()), "nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw(x, out=None):
+    B, H, W, C = x.shape
+    y = out if out is not None else torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    N.check(N.lib().fpd_nhwc_to_nchw(_p(x), _p(y), B, C, H, W, _stream()), "nhwc_to_nchw")
+    return y
+
+
+def add(a, b, out=None):
+    o = out if out is not None else torch.empty_like(a)
+    N.check(N.lib().fpd_add(_p(a), _p(b), _p(o), a.numel(), _stream()), "add")
+    return o
+
+
+def fpd_loss(outs_nhwc, target_nchw, teacher_nhwc, target_weight, alpha, want_grads=True, grad_scale=1.0,
+             grads_out=None, losses_out=None):
+    """Fused FPD loss. outs_nhwc: list of [B,h,w,J]; returns (losses[3] device tensor, grads list or None)."""
+    S = len(outs_nhwc)
+    B, h, w, J = outs_nhwc[0].shape
+    dev = outs_nhwc[0].device
+    tw = target_weight.reshape(B, J).contiguous()
+    losses = losses_out if losses_out is not None else torch.empty(3, dtype=torch.float32, device=dev)
+    grads = None
+    if want_grads:
+        grads = grads_out if grads_out is not None else [torch.empty_like(o) for o in outs_nhwc]
+    outs_arr = (ctypes.c_void_p * S)(*[o.data_ptr() for o in outs_nhwc])
+    grads_arr = (ctypes.c_void_p * S)(*[g.data_ptr() for g in grads]) if grads is not None else None
+    ws = _ws.get(N.lib().fpd_loss_workspace_bytes(B, J, h, w), dev)
+    N.check(N.lib().fpd_loss_fused(outs_arr, S, _p(target_nchw), _p(teacher_nhwc), _p(tw), float(alpha), grads_arr,
+                                   float(grad_scale), _p(losses), B, J, h, w, _p(ws), ws.numel(), _stream()),
+            "loss_fused")
+    return losses, grads
+
+
+def joints_mse(out_nchw, target_nchw, target_weight=None, want_grad=True):
+    B, J = out_nchw.shape[:2]
+    hw = out_nchw.numel() // (B * J)
+    dev = out_nchw.device
+    loss3 = torch.empty(3, dtype=torch.float32, device=dev)
+    grad = torch.empty_like(out_nchw) if want_grad else None
+    tw = None if target_weight is None else target_weight.reshape(B, J).contiguous()
+    ws = _ws.get(1 << 16, dev)
+    N.check(N.lib().fpd_joints_mse(_p(out_nchw), _p(target_nchw), _p(tw), _p(loss3), _p(grad), B, J, hw, _p(ws),
+                                   ws.numel(), _stream()), "joints_mse")
+    return loss3, grad
+
+
+def flip_merge_argmax(hm_nhwc, hm_flip_nhwc=None, flip_perm=None, shift=False, want_avg=True):
+    B, h, w, J = hm_nhwc.shape
+    dev = hm_nhwc.device
+    avg = torch.empty_like(hm_nhwc) if want_avg else None
+    idx = torch.empty((B, J), dtype=torch.int32, device=dev)
+    maxval = torch.empty((B, J), dtype=torch.float32, device=dev)
+    N.check(N.lib().fpd_flip_merge_argmax(_p(hm_nhwc), _p(hm_flip_nhwc), _p(flip_perm), int(shift), _p(avg), _p(idx),
+                                          _p(maxval), B, J, h, w, _stream()), "flip_merge_argmax")
+    return avg, idx, maxval
+
+
+def argmax_nchw(hm):
+    B, J = hm.shape[:2]
+    hw = hm.numel() // (B * J)
+    idx = torch.empty((B, J), dtype=torch.int32, device=hm.device)
+    maxval = torch.empty((B, J), dtype=torch.float32, device=hm.device)
+    N.check(N.lib().fpd_argmax_nchw(_p(hm), _p(idx), _p(maxval), B * J, hw, _stream()), "argmax_nchw")
+    return idx, maxval
+
+
+def nms_device(boxes_sorted, thresh):
+    n, d = boxes_sorted.shape
+    dev = boxes_sorted.device
+    keep = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    num = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _ws.get(N.lib().fpd_nms_workspace_bytes(n), dev)
+    N.check(N.lib().fpd_nms_device(_p(boxes_sorted), n, d, float(thresh), _p(keep), _p(num), _p(ws), ws.numel(),
+                                   _stream()), "nms_device")
+    return keep, num
+
+
+def adam_flat(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    N.check(N.lib().fpd_adam_flat(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr),
+                                  float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                                  float(grad_scale), _stream()), "adam_flat")

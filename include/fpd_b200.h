@@ -1,0 +1,174 @@
+/* fpd_b200.h -- C ABI of libfpd_b200.so: the B200 (sm_100a) kernels behind the reference's hot path
+ * (ilovepose/fast-human-pose-estimation.pytorch: stacked-hourglass / HRNet heat-map regression with the
+ * Fast-Pose-Distillation loss, flip-test decode, box NMS).
+ *
+ * Conventions (all entry points):
+ *  - plain pointers and sizes, no torch types; every tensor is caller-owned DEVICE memory unless the
+ *    parameter name ends in `_host`; the library never allocates or frees device memory at call time
+ *    (scratch comes in through `workspace`, sized by the matching *_workspace_bytes query). The one
+ *    exception is fpd_nms_host, which keeps the reference `_nms` signature (no workspace argument) and
+ *    therefore owns a grow-only scratch buffer.
+ *  - work is enqueued on `stream` only (pass torch.cuda.current_stream().cuda_stream); no implicit
+ *    device synchronisation, no default-stream use, safe under CUDA-graph capture.
+ *  - return 0 on success, a negative FPD_ERR_* code otherwise; fpd_last_error() gives the message of the
+ *    last failure on the calling thread. Nothing prints-and-continues (contrast the reference's
+ *    CUDA_CHECK, lib/nms/nms_kernel.cu:11-18).
+ *  - activations are NHWC fp32 ("[B,H,W,C]", C contiguous); conv weights are the reference's OIHW fp32
+ *    unless stated; heat-maps handed to/from callers are NCHW like the reference's.
+ *
+ * Each group cites the reference interface it replaces (paths relative to the reference repo).
+ */
+#ifndef FPD_B200_H_
+#define FPD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* fpd_stream_t;
+
+#define FPD_OK 0
+#define FPD_ERR_INVALID (-1)
+#define FPD_ERR_CUDA (-2)
+#define FPD_ERR_UNSUPPORTED (-3)
+
+const char* fpd_last_error(void);
+int fpd_version(void);
+int fpd_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Convolution. Replaces nn.Conv2d -> cuDNN/oneDNN as used by lib/models/hourglass.py:20-27 (Bottleneck
+ * conv1/conv2/conv3), :116 (7x7 stem), :134-137,149,163 (fc / score / fc_ / score_ / downsample) and
+ * lib/models/pose_hrnet.py:23-25 (conv3x3), :33-37,66-74.
+ * ------------------------------------------------------------------------------------------------- */
+
+/* 1 if (Cin, Cout, ksize) is handled by the tcgen05 kernels (ksize in {1,3}, stride 1, "same" pad). */
+int fpd_conv2d_tc_supported(int Cin, int Cout, int ksize);
+
+/* Tensor-core implicit GEMM, forward or data-gradient (dgrad = same call on dY with weights prepared
+ * by fpd_weight_prep(for_dgrad=1)).
+ *   y[B,H,W,Cout] = out_scale * conv(a, w) (+ bias[Cout]) (+ residual[B,H,W,Cout]); if relu_mask is
+ *   given (same shape as y) elements with relu_mask <= 0 are written as 0 (ReLU backward fused).
+ *   a_hi/a_lo : NHWC tf32 hi/lo operand pair from fpd_affine_act_split (a_lo NULL => single-pass TF32,
+ *               then w_lo must be NULL too; both non-NULL => 3xTF32, fp32-grade accuracy)
+ *   w_hi/w_lo : [ksize*ksize][Cout][Cin] from fpd_weight_prep */
+int fpd_conv2d_tc(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, const float* bias,
+                  const float* residual, const float* relu_mask, float* y, float out_scale, int B, int H, int W,
+                  int Cin, int Cout, int ksize, fpd_stream_t stream);
+
+/* Tensor-core weight gradient: dw_oihw[Cout,Cin,k,k] = scale * sum_pixels dy (x) a(tap-shifted). */
+int fpd_conv2d_wgrad_tc_supported(int Cin, int Cout, int ksize);
+size_t fpd_conv2d_wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize);
+int fpd_conv2d_wgrad_tc(const float* a_hi, const float* a_lo, const float* dy_hi, const float* dy_lo,
+                        float* dw_oihw, float scale, int B, int H, int W, int Cin, int Cout, int ksize,
+                        void* workspace, size_t workspace_bytes, fpd_stream_t stream);
+
+/* Generic fp32 CUDA-core convolution (any k/stride/pad): x NHWC [B,H,W,Cin], w OIHW. */
+int fpd_conv2d_simt_fwd(const float* x, const float* w_oihw, const float* bias, const float* residual, float* y,
+                        int B, int H, int W, int Cin, int Cout, int k, int stride, int pad, fpd_stream_t stream);
+int fpd_conv2d_simt_dgrad(const float* dy, const float* w_oihw, float* dx, int B, int H, int W, int Cin, int Cout,
+                          int k, int stride, int pad, fpd_stream_t stream);
+int fpd_conv2d_simt_wgrad(const float* x, const float* dy, float* dw_oihw, float scale, int B, int H, int W,
+                          int Cin, int Cout, int k, int stride, int pad, fpd_stream_t stream);
+
+/* OIHW fp32 -> tensor-core operand layout, split into tf32 hi/lo (w_lo may be NULL).
+ * for_dgrad=0: [tap][O][I]; for_dgrad=1: [taps-1-tap][I][O] (180-degree flipped, transposed). */
+int fpd_weight_prep(const float* w_oihw, float* w_hi, float* w_lo, int O, int I, int k, int for_dgrad,
+                    fpd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * BatchNorm / ReLU / pooling glue. Replaces nn.BatchNorm2d (train + eval), nn.ReLU, F.max_pool2d,
+ * nn.Upsample(scale_factor=2) + add: lib/models/hourglass.py:18-28,34-50,60,82-91,117-124.
+ * ------------------------------------------------------------------------------------------------- */
+size_t fpd_bn_stats_workspace_bytes(int64_t P, int C);
+/* per-channel batch mean and biased variance of x[P,C] */
+int fpd_bn_stats(const float* x, int64_t P, int C, float* mean, float* var_biased, void* workspace,
+                 size_t workspace_bytes, fpd_stream_t stream);
+/* scale = gamma/sqrt(var+eps), shift = beta - mean*scale, invstd (optional); running stats (optional,
+ * both or neither) updated with `momentum` and the unbiased variance like nn.BatchNorm2d. */
+int fpd_bn_finalize(const float* mean, const float* var_biased, const float* gamma, const float* beta, float eps,
+                    int64_t count, float* scale, float* shift, float* invstd, float* running_mean,
+                    float* running_var, float momentum, int C, fpd_stream_t stream);
+/* a = relu?(x*scale+shift) (scale/shift NULL = identity) -> a_hi = tf32(a), a_lo = tf32(a - a_hi) (optional) */
+int fpd_affine_act_split(const float* x, const float* scale, const float* shift, int relu, float* a_hi,
+                         float* a_lo, int64_t P, int C, fpd_stream_t stream);
+size_t fpd_channel_reduce_workspace_bytes(int64_t P, int C);
+int fpd_channel_sum(const float* dy, int64_t P, int C, float scale, float* out, void* workspace,
+                    size_t workspace_bytes, fpd_stream_t stream);
+/* BN(+ReLU) backward: phase 1 reduces sums[0:C]=sum dz, sums[C:2C]=sum dz*xhat; phase 2 writes
+ * dx (= or +=) gamma*invstd*(dz - sum_dz/P - xhat*sum_dzxhat/P). dbeta = sums[0:C], dgamma = sums[C:2C]. */
+int fpd_bn_bwd_reduce(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
+                      const float* shift, int relu, int64_t P, int C, float* sums, void* workspace,
+                      size_t workspace_bytes, fpd_stream_t stream);
+int fpd_bn_bwd_apply(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
+                     const float* shift, const float* gamma, int relu, const float* sums, int accumulate, float* dx,
+                     int64_t P, int C, fpd_stream_t stream);
+int fpd_affine_act_bwd(const float* da, const float* x, const float* scale, const float* shift, int relu,
+                       int accumulate, float* dx, int64_t P, int C, fpd_stream_t stream);
+int fpd_maxpool2x2_fwd(const float* x, float* y, int B, int H, int W, int C, fpd_stream_t stream);
+int fpd_maxpool2x2_bwd(const float* x, const float* dy, float* dx, int accumulate, int B, int H, int W, int C,
+                       fpd_stream_t stream);
+int fpd_upsample2x_add(const float* up1, const float* low, float* out, int B, int H, int W, int C,
+                       fpd_stream_t stream); /* H,W = output size */
+int fpd_upsample2x_bwd(const float* dout, float* dlow, int B, int H, int W, int C, fpd_stream_t stream);
+int fpd_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, fpd_stream_t stream);
+int fpd_nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, fpd_stream_t stream);
+int fpd_add(const float* a, const float* b, float* out, int64_t n, fpd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Loss. Replaces lib/core/loss.py:21-39 (JointsMSELoss) and the FPD combination in
+ * lib/core/function.py:127-134: loss = (1-alpha)*sum_s L(out_s,target) + alpha*sum_s L(out_s,teacher).
+ * ------------------------------------------------------------------------------------------------- */
+size_t fpd_loss_workspace_bytes(int B, int J, int h, int w);
+/* outs_host / grads_host: HOST arrays of S device pointers (NHWC [B,h,w,J]); grads_host or its entries
+ * may be NULL. target: NCHW [B,J,h,w]; teacher: NHWC or NULL (plain sum-of-stacks MSE, function.py:44-55);
+ * target_weight [B,J]; losses[3] (device) = {pose, kd, total}; grads = grad_scale * dtotal/dout_s. */
+int fpd_loss_fused(const float* const* outs_host, int S, const float* target_nchw, const float* teacher_nhwc,
+                   const float* target_weight, float alpha, float* const* grads_host, float grad_scale,
+                   float* losses, int B, int J, int h, int w, void* workspace, size_t workspace_bytes,
+                   fpd_stream_t stream);
+/* single JointsMSELoss on NCHW tensors; loss3 (device, 3 floats, [0] is the loss); grad (optional) =
+ * dloss/dout; target_weight NULL = use_target_weight False. */
+int fpd_joints_mse(const float* out_nchw, const float* target_nchw, const float* target_weight, float* loss3,
+                   float* grad, int B, int J, int hw, void* workspace, size_t workspace_bytes, fpd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Decode. Replaces the numpy round-trips of lib/core/function.py:218-240 (flip test),
+ * lib/utils/transforms.py:15-29 (flip_back) and lib/core/inference.py:18-46 (get_max_preds).
+ * ------------------------------------------------------------------------------------------------- */
+/* hm, hm_flip: NHWC [B,h,w,J] (hm_flip NULL = no flip test); flip_perm[J] device int32 (joint j of the
+ * flipped map comes from channel flip_perm[j]); avg_nhwc optional output; idx[B*J] flat arg-max
+ * (first maximum), maxval[B*J]. */
+int fpd_flip_merge_argmax(const float* hm, const float* hm_flip, const int* flip_perm, int shift, float* avg_nhwc,
+                          int* idx, float* maxval, int B, int J, int h, int w, fpd_stream_t stream);
+int fpd_argmax_nchw(const float* hm_nchw, int* idx, float* maxval, int BJ, int hw, fpd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * NMS. Replaces lib/nms/nms_kernel.cu:33-77 (nms_kernel) and :90-143 (_nms), declared in
+ * lib/nms/gpu_nms.hpp:1-2.
+ * ------------------------------------------------------------------------------------------------- */
+size_t fpd_nms_workspace_bytes(int n);
+/* boxes: device [n,box_dim] sorted by score descending; keep/num_keep: device outputs */
+int fpd_nms_device(const float* boxes_sorted, int n, int box_dim, float thresh, int* keep, int* num_keep,
+                   void* workspace, size_t workspace_bytes, fpd_stream_t stream);
+/* Drop-in for `void _nms(int* keep_out, int* num_out, const float* boxes_host, int boxes_num,
+ * int boxes_dim, float nms_overlap_thresh, int device_id)` (host pointers, synchronous) -- but it
+ * returns an error code instead of printing. */
+int fpd_nms_host(int* keep_out_host, int* num_out_host, const float* boxes_host, int boxes_num, int boxes_dim,
+                 float nms_overlap_thresh, int device_id);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Optimizer. Replaces torch.optim.Adam as configured by lib/utils/utils.py:69-73, stepped at
+ * lib/core/function.py:147, over one flat parameter buffer.
+ * ------------------------------------------------------------------------------------------------- */
+int fpd_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                  fpd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPD_B200_H_ */

@@ -1,0 +1,325 @@
+"""GPU parity of every C-ABI op against a plain PyTorch fp32 composition of the same op
+(TF32 disabled in the torch reference). The network-level parity against the reference model lives in
+test_hourglass_gpu.py; this file pins each kernel in isolation."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _fp32_reference_mode():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def ops():
+    from fpd_b200 import ops as o
+    return o
+
+
+def relerr(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+def nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x_nhwc):
+    return x_nhwc.permute(0, 3, 1, 2).contiguous()
+
+
+CONV_TC_SHAPES = [
+    # B, H, W, Cin, Cout, k
+    (2, 64, 64, 64, 64, 3),
+    (2, 64, 64, 128, 64, 1),
+    (2, 64, 64, 64, 128, 1),
+    (4, 32, 32, 64, 64, 3),
+    (4, 16, 16, 64, 64, 3),
+    (8, 8, 8, 64, 64, 3),
+    (8, 4, 4, 64, 64, 3),
+    (2, 4, 4, 64, 64, 3),      # batch smaller than the pixel-tile's image count
+    (3, 8, 8, 128, 64, 1),     # ragged last tile
+    (2, 128, 128, 32, 32, 3),
+    (2, 64, 64, 128, 16, 1),   # score conv
+    (2, 64, 64, 128, 128, 1),
+    (1, 64, 64, 128, 256, 1),
+    (1, 64, 64, 256, 256, 1),  # teacher fc
+    (1, 32, 32, 128, 128, 3),  # teacher 3x3
+    (2, 64, 48, 32, 32, 3),    # HRNet resolution (W not a power of two)
+    (2, 16, 12, 128, 128, 3),
+]
+
+
+@pytest.mark.parametrize("shape", CONV_TC_SHAPES)
+@pytest.mark.parametrize("passes", [3, 1])
+def test_conv2d_tc_forward(shape, passes):
+    B, H, W, Cin, Cout, k = shape
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * (1.0 / (Cin * k * k) ** 0.5)
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(B, Cout, H, W, device="cuda", generator=g)
+    ref = F.conv2d(x, w, bias, padding=k // 2) + res
+    a_hi, a_lo = o.affine_act_split(nhwc(x), split=(passes == 3))
+    w_hi, w_lo = o.weight_prep(w, split=(passes == 3))
+    y = o.conv2d_tc(a_hi, a_lo, w_hi, w_lo, k, bias=bias, residual=nhwc(res))
+    torch.cuda.synchronize()
+    err = relerr(nchw(y), ref)
+    assert err < (2e-6 if passes == 3 else 3e-3), "conv_tc %s passes=%d rel err %.3e" % (shape, passes, err)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 64, 64, 3), (2, 32, 32, 128, 64, 1), (4, 8, 8, 64, 128, 1)])
+def test_conv2d_tc_dgrad_with_relu_mask(shape):
+    B, H, W, Cin, Cout, k = shape
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g, requires_grad=True)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * 0.05
+    a = F.relu(x)
+    y = F.conv2d(a, w, None, padding=k // 2)
+    dy = torch.randn_like(y)
+    (dx_ref,) = torch.autograd.grad(y, x, dy)
+    wd_hi, wd_lo = o.weight_prep(w, for_dgrad=True)
+    dy_hi, dy_lo = o.affine_act_split(nhwc(dy))
+    mask = nhwc(a.detach())
+    dx = o.conv2d_tc(dy_hi, dy_lo, wd_hi, wd_lo, k, relu_mask=mask)
+    torch.cuda.synchronize()
+    assert relerr(nchw(dx), dx_ref) < 2e-6
+
+
+@pytest.mark.parametrize("cfg", [
+    # B, H, W, Cin, Cout, k, stride, pad
+    (2, 64, 64, 3, 32, 7, 2, 3),
+    (2, 16, 16, 16, 128, 1, 1, 0),
+    (2, 16, 16, 128, 16, 1, 1, 0),
+    (2, 12, 10, 8, 12, 3, 2, 1),
+    (1, 9, 9, 5, 7, 3, 1, 1),
+])
+def test_conv2d_simt(cfg):
+    B, H, W, Cin, Cout, k, stride, pad = cfg
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g, requires_grad=True)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g, requires_grad=True)
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    y_ref = F.conv2d(x, w, bias, stride=stride, padding=pad)
+    dy = torch.randn_like(y_ref)
+    dx_ref, dw_ref = torch.autograd.grad(y_ref, (x, w), dy)
+    y = o.conv2d_simt_fwd(nhwc(x.detach()), w.detach(), bias=bias, stride=stride, pad=pad)
+    dx = o.conv2d_simt_dgrad(nhwc(dy), w.detach(), (H, W), stride=stride, pad=pad)
+    dw = o.conv2d_simt_wgrad(nhwc(x.detach()), nhwc(dy), k, stride=stride, pad=pad)
+    torch.cuda.synchronize()
+    assert relerr(nchw(y), y_ref) < 1e-5
+    assert relerr(nchw(dx), dx_ref) < 1e-5
+    assert relerr(dw, dw_ref) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 64, 128), (32, 4, 4, 64), (3, 16, 12, 48), (2, 128, 128, 32), (2, 8, 8, 256)])
+def test_bn_train_forward_backward(shape):
+    B, H, W, C = shape
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    # large common-mode offset: the cancellation-prone case for E[x^2]-E[x]^2
+    x = (torch.randn(B, C, H, W, device="cuda", generator=g) * 0.3 + 25.0).requires_grad_(True)
+    gamma = (torch.rand(C, device="cuda", generator=g) + 0.5).requires_grad_(True)
+    beta = torch.randn(C, device="cuda", generator=g).requires_grad_(True)
+    rm = torch.zeros(C, device="cuda"); rv = torch.ones(C, device="cuda")
+    rm2 = rm.clone(); rv2 = rv.clone()
+    y_ref = F.relu(F.batch_norm(x, rm, rv, gamma, beta, True, 0.1, 1e-5))
+    dy = torch.randn_like(y_ref)
+    dx_ref, dg_ref, db_ref = torch.autograd.grad(y_ref, (x, gamma, beta), dy)
+
+    xh = nhwc(x.detach())
+    mean, var = o.bn_stats(xh)
+    scale, shift, invstd = o.bn_finalize(mean, var, gamma.detach(), beta.detach(), 1e-5, B * H * W, rm2, rv2, 0.1)
+    a_hi, a_lo = o.affine_act_split(xh, scale, shift, relu=True)
+    dx, dgamma, dbeta = o.bn_bwd(nhwc(dy), xh, mean, invstd, scale, shift, gamma.detach(), True)
+    torch.cuda.synchronize()
+    xd = x.detach().double()
+    assert relerr(mean, xd.mean((0, 2, 3)).float()) < 1e-6
+    assert relerr(var, xd.var((0, 2, 3), unbiased=False).float()) < 1e-5
+    assert relerr(rm2, rm) < 1e-6 and relerr(rv2, rv) < 1e-5
+    assert relerr(nchw(a_hi + a_lo), y_ref) < 1e-5
+    assert relerr(nchw(dx), dx_ref) < 1e-4
+    assert relerr(dgamma, dg_ref) < 1e-4 and relerr(dbeta, db_ref) < 1e-4
+
+
+def test_split_is_exact_tf32_pair():
+    o = ops()
+    x = torch.randn(8, 8, 8, 32, device="cuda") * 3
+    hi, lo = o.affine_act_split(x)
+    torch.cuda.synchronize()
+    # both parts have their low 13 mantissa bits clear and hi+lo reproduces x to ~2^-21
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert int((lo.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert relerr(hi + lo, x) < 1e-6
+
+
+def test_pool_upsample_layout_add():
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(3, 64, 16, 12, device="cuda", generator=g, requires_grad=True)
+    y_ref = F.max_pool2d(x, 2, stride=2)
+    dy = torch.randn_like(y_ref)
+    (dx_ref,) = torch.autograd.grad(y_ref, x, dy)
+    xh = nhwc(x.detach())
+    y = o.maxpool2x2(xh)
+    dx = o.maxpool2x2_bwd(xh, nhwc(dy))
+    base = torch.randn_like(xh)
+    dx_acc = o.maxpool2x2_bwd(xh, nhwc(dy), accumulate_into=base.clone())
+    up1 = torch.randn(3, 64, 16, 12, device="cuda", generator=g)
+    low = torch.randn(3, 64, 8, 6, device="cuda", generator=g)
+    out_ref = up1 + F.interpolate(low, scale_factor=2, mode="nearest")
+    out = o.upsample2x_add(nhwc(up1), nhwc(low))
+    dlow = o.upsample2x_bwd(nhwc(up1))
+    dlow_ref = F.avg_pool2d(up1, 2) * 4
+    torch.cuda.synchronize()
+    assert torch.equal(nchw(y), y_ref)
+    assert torch.equal(nchw(dx), dx_ref)
+    assert relerr(dx_acc, base + nhwc(dx_ref)) < 1e-6
+    assert relerr(nchw(out), out_ref) < 1e-7
+    assert relerr(nchw(dlow), dlow_ref) < 1e-6
+    z = torch.randn(2, 17, 64, 48, device="cuda")
+    assert torch.equal(o.nchw_to_nhwc(z), nhwc(z))
+    assert torch.equal(o.nhwc_to_nchw(nhwc(z)), z)
+    assert torch.equal(o.add(z, z), z + z)
+    assert relerr(o.channel_sum(nhwc(x.detach())), x.detach().sum((0, 2, 3))) < 1e-5
+
+
+def _ref_joints_mse(output, target, tw):
+    # closed form of lib/core/loss.py:21-39 (checked against the reference module in tests/test_oracle.py)
+    B, J = output.shape[:2]
+    d = (output - target).reshape(B, J, -1) * tw.reshape(B, J, 1)
+    return 0.5 * (d ** 2).mean(dim=(0, 2)).sum() / J
+
+
+@pytest.mark.parametrize("S,B,J,h,w,teacher", [(4, 4, 16, 64, 64, True), (1, 2, 16, 64, 64, False), (2, 3, 17, 64, 48, True)])
+def test_fpd_loss_fused(S, B, J, h, w, teacher):
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    outs = [torch.randn(B, J, h, w, device="cuda", generator=g, requires_grad=True) for _ in range(S)]
+    target = torch.rand(B, J, h, w, device="cuda", generator=g)
+    t = torch.randn(B, J, h, w, device="cuda", generator=g) if teacher else None
+    tw = (torch.rand(B, J, 1, device="cuda", generator=g) > 0.2).float() * (1 + torch.rand(B, J, 1, device="cuda", generator=g))
+    alpha = 0.5
+    pose = sum(_ref_joints_mse(x, target, tw) for x in outs)
+    if teacher:
+        kd = sum(_ref_joints_mse(x, t, tw) for x in outs)
+        loss = (1 - alpha) * pose + alpha * kd
+    else:
+        kd = torch.zeros(())
+        loss = pose
+    grads_ref = torch.autograd.grad(loss, outs)
+    losses, grads = o.fpd_loss([nhwc(x.detach()) for x in outs], target, nhwc(t) if teacher else None, tw, alpha)
+    torch.cuda.synchronize()
+    assert abs(losses[0].item() - pose.item()) <= 1e-5 * abs(pose.item())
+    if teacher:
+        assert abs(losses[1].item() - kd.item()) <= 1e-5 * abs(kd.item())
+    assert abs(losses[2].item() - loss.item()) <= 1e-5 * abs(loss.item())
+    for gm, gr in zip(grads, grads_ref):
+        assert relerr(nchw(gm), gr) < 1e-5
+
+
+def test_joints_mse_nchw():
+    o = ops()
+    out = torch.randn(4, 16, 64, 64, device="cuda", requires_grad=True)
+    tgt = torch.rand(4, 16, 64, 64, device="cuda")
+    tw = torch.rand(4, 16, 1, device="cuda")
+    ref = _ref_joints_mse(out, tgt, tw)
+    (g_ref,) = torch.autograd.grad(ref, out)
+    loss3, grad = o.joints_mse(out.detach(), tgt, tw)
+    torch.cuda.synchronize()
+    assert abs(loss3[0].item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert relerr(grad, g_ref) < 1e-5
+
+
+def test_flip_merge_argmax_bit_exact():
+    o = ops()
+    B, J, h, w = 6, 16, 64, 64
+    g = torch.Generator(device="cuda").manual_seed(21)
+    hm = torch.randn(B, J, h, w, device="cuda", generator=g)
+    hf = torch.randn(B, J, h, w, device="cuda", generator=g)
+    hm[0, 0] = 0.25  # constant map: first index must win
+    hf[0, 0] = 0.25
+    pairs = [[0, 5], [1, 4], [2, 3], [10, 15], [11, 14], [12, 13]]
+    perm = list(range(J))
+    for a, b in pairs:
+        perm[a], perm[b] = b, a
+    # numpy restatement of function.py:218-240 + transforms.py:15-29 + inference.py:18-46
+    f = hf.cpu().numpy()[:, :, :, ::-1].copy()
+    for a, b in pairs:
+        tmp = f[:, a].copy(); f[:, a] = f[:, b]; f[:, b] = tmp
+    f[:, :, :, 1:] = f.copy()[:, :, :, 0:-1]
+    merged = (hm.cpu().numpy() + f) * np.float32(0.5)
+    idx_ref = merged.reshape(B, J, -1).argmax(2)
+    max_ref = merged.reshape(B, J, -1).max(2)
+    avg, idx, maxval = o.flip_merge_argmax(nhwc(hm), nhwc(hf), torch.tensor(perm, dtype=torch.int32, device="cuda"), shift=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(nchw(avg).cpu().numpy(), merged)
+    assert np.array_equal(idx.cpu().numpy(), idx_ref)
+    assert np.array_equal(maxval.cpu().numpy(), max_ref)
+    idx2, max2 = o.argmax_nchw(hm)
+    assert np.array_equal(idx2.cpu().numpy(), hm.cpu().numpy().reshape(B, J, -1).argmax(2))
+
+
+def _nms_numpy(dets, thresh):
+    # restatement of lib/nms/nms.py:35-72
+    x1, y1, x2, y2, scores = dets[:, 0], dets[:, 1], dets[:, 2], dets[:, 3], dets[:, 4]
+    areas = (x2 - x1 + 1) * (y2 - y1 + 1)
+    order = scores.argsort()[::-1]
+    keep = []
+    while order.size > 0:
+        i = order[0]
+        keep.append(i)
+        xx1 = np.maximum(x1[i], x1[order[1:]]); yy1 = np.maximum(y1[i], y1[order[1:]])
+        xx2 = np.minimum(x2[i], x2[order[1:]]); yy2 = np.minimum(y2[i], y2[order[1:]])
+        ww = np.maximum(0.0, xx2 - xx1 + 1); hh = np.maximum(0.0, yy2 - yy1 + 1)
+        inter = ww * hh
+        ovr = inter / (areas[i] + areas[order[1:]] - inter)
+        order = order[np.where(ovr <= thresh)[0] + 1]
+    return keep
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 1000, 4096])
+def test_nms_matches_numpy(n):
+    o = ops()
+    rng = np.random.RandomState(n)
+    x1 = rng.uniform(0, 256, n); y1 = rng.uniform(0, 256, n)
+    bw = rng.uniform(8, 128, n); bh = rng.uniform(8, 128, n)
+    dets = np.stack([x1, y1, x1 + bw, y1 + bh, rng.uniform(0, 1, n)], 1).astype(np.float32)
+    keep_ref = _nms_numpy(dets, 0.6)
+    order = dets[:, 4].argsort()[::-1]
+    sorted_dets = torch.from_numpy(dets[order].copy()).cuda()
+    keep, num = o.nms_device(sorted_dets, 0.6)
+    torch.cuda.synchronize()
+    k = keep[: int(num.item())].cpu().numpy()
+    assert list(order[k]) == list(keep_ref)
+    # host-pointer drop-in for `_nms`
+    import ctypes
+    from fpd_b200 import _native as N
+    keep_h = np.zeros(n, dtype=np.int32); num_h = ctypes.c_int(0)
+    sd = np.ascontiguousarray(dets[order])
+    N.check(N.lib().fpd_nms_host(keep_h.ctypes.data_as(ctypes.c_void_p), ctypes.cast(ctypes.byref(num_h), ctypes.c_void_p),
+                                 sd.ctypes.data_as(ctypes.c_void_p), n, 5, 0.6, 0))
+    assert list(order[keep_h[: num_h.value]]) == list(keep_ref)
+
+
+def test_adam_flat_matches_torch():
+    o = ops()
+    p = torch.randn(10007, device="cuda")
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=2.5e-4)
+    m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in range(1, 4):
+        gr = torch.randn_like(p)
+        ref.grad = gr.clone()
+        opt.step()
+        o.adam_flat(p, gr, m, v, 2.5e-4, 0.9, 0.999, 1e-8, 0.0, step)
+    torch.cuda.synchronize()
+    assert relerr(p, ref.detach()) < 1e-6
