@@ -127,9 +127,13 @@ int fpd_bn_finalize(const float* mean, const float* var, const float* gamma, con
                     float momentum, int C, fpd_stream_t stream) {
   return bn_finalize(mean, var, gamma, beta, eps, count, scale, shift, invstd, rmean, rvar, momentum, C, S(stream));
 }
-int fpd_affine_act_split(const float* x, const float* scale, const float* shift, int relu, float* a_hi, float* a_lo,
-                         int64_t P, int C, fpd_stream_t stream) {
-  return affine_act_split(x, scale, shift, relu, a_hi, a_lo, P, C, S(stream));
+int fpd_affine_act_split(const float* x, const float* mean, const float* scale, const float* shift, int relu,
+                         float* a_hi, float* a_lo, int64_t P, int C, fpd_stream_t stream) {
+  return affine_act_split(x, mean, scale, shift, relu, a_hi, a_lo, P, C, S(stream));
+}
+int fpd_affine_act(const float* x, const float* mean, const float* scale, const float* shift, int relu, float* y,
+                   int64_t P, int C, fpd_stream_t stream) {
+  return affine_act(x, mean, scale, shift, relu, y, P, C, S(stream));
 }
 size_t fpd_channel_reduce_workspace_bytes(int64_t P, int C) { return channel_reduce_workspace_bytes(P, C); }
 int fpd_channel_sum(const float* dy, int64_t P, int C, float scale, float* out, void* ws, size_t wsb,
@@ -146,9 +150,9 @@ int fpd_bn_bwd_apply(const float* da, const float* x, const float* mean, const f
                      int64_t P, int C, fpd_stream_t stream) {
   return bn_bwd_apply(da, x, mean, invstd, scale, shift, gamma, relu, sums, accumulate, dx, P, C, S(stream));
 }
-int fpd_affine_act_bwd(const float* da, const float* x, const float* scale, const float* shift, int relu,
-                       int accumulate, float* dx, int64_t P, int C, fpd_stream_t stream) {
-  return affine_act_bwd(da, x, scale, shift, relu, accumulate, dx, P, C, S(stream));
+int fpd_affine_act_bwd(const float* da, const float* x, const float* mean, const float* scale, const float* shift,
+                       int relu, int accumulate, float* dx, int64_t P, int C, fpd_stream_t stream) {
+  return affine_act_bwd(da, x, mean, scale, shift, relu, accumulate, dx, P, C, S(stream));
 }
 int fpd_maxpool2x2_fwd(const float* x, float* y, int B, int H, int W, int C, fpd_stream_t stream) {
   return maxpool2x2_fwd(x, y, B, H, W, C, S(stream));

@@ -136,7 +136,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ mean, const float* 
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
   const float sc = g * invstd;
   scale[c] = sc;
-  shift[c] = b - m * sc;
+  shift[c] = b;  // centred form: y = (x - mean) * scale + shift
   if (invstd_out) invstd_out[c] = invstd;
   if (rmean) {
     rmean[c] = (1.f - momentum) * rmean[c] + momentum * m;
@@ -234,7 +234,7 @@ struct BnBwdFunctor {
                 ie[4] = {is.x, is.y, is.z, is.w}, se[4] = {sc.x, sc.y, sc.z, sc.w}, he[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const bool on = !relu || (fmaf(xe[j], se[j], he[j]) > 0.f);
+      const bool on = !relu || (fmaf(xe[j] - me[j], se[j], he[j]) > 0.f);
       const float dz = on ? ge[j] : 0.f;
       v[0][j] = dz;
       v[1][j] = dz * ((xe[j] - me[j]) * ie[j]);
@@ -245,20 +245,26 @@ struct BnBwdFunctor {
 // -------------------------------------------------------------------------------------------------
 // pointwise kernels
 // -------------------------------------------------------------------------------------------------
-__global__ void affine_act_split_kernel(const float4* __restrict__ x, const float* __restrict__ scale,
+__global__ void affine_act_split_kernel(const float4* __restrict__ x, const float* __restrict__ mean,
+                                        const float* __restrict__ scale,
                                         const float* __restrict__ shift, int relu, float4* __restrict__ hi,
-                                        float4* __restrict__ lo, int64_t n4, int L) {
+                                        float4* __restrict__ lo, int64_t n4, int L, int round) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = __ldg(x + i);
     if (scale) {
       const int cx = (int)(i % L);
       const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cx);
       const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cx);
-      v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-      v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+      const float4 mu = mean ? __ldg(reinterpret_cast<const float4*>(mean) + cx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v.x = fmaf(v.x - mu.x, sc.x, sh.x); v.y = fmaf(v.y - mu.y, sc.y, sh.y);
+      v.z = fmaf(v.z - mu.z, sc.z, sh.z); v.w = fmaf(v.w - mu.w, sc.w, sh.w);
     }
     if (relu) {
       v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    }
+    if (!round) {
+      hi[i] = v;
+      continue;
     }
     float4 h, l;
     split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
@@ -291,7 +297,7 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ da, const float4*
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const bool on = !relu || (fmaf(xe[j], se[j], he[j]) > 0.f);
+      const bool on = !relu || (fmaf(xe[j] - me[j], se[j], he[j]) > 0.f);
       const float dz = on ? ge[j] : 0.f;
       const float xh = (xe[j] - me[j]) * ie[j];
       o[j] = ga[j] * ie[j] * (dz - a0[j] * inv_count - xh * a1[j] * inv_count);
@@ -306,23 +312,24 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ da, const float4*
 }
 
 __global__ void affine_act_bwd_kernel(const float4* __restrict__ da, const float4* __restrict__ x,
-                                      const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                                      const float* __restrict__ mean, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                                       int accumulate, float4* __restrict__ dx, int64_t n4, int L) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int cx = (int)(i % L);
     const float4 g = __ldg(da + i);
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), mu = sh;
     if (scale) {
       sc = __ldg(reinterpret_cast<const float4*>(scale) + cx);
       sh = __ldg(reinterpret_cast<const float4*>(shift) + cx);
+      if (mean) mu = __ldg(reinterpret_cast<const float4*>(mean) + cx);
     }
     float4 r = make_float4(g.x * sc.x, g.y * sc.y, g.z * sc.z, g.w * sc.w);
     if (relu) {
       const float4 xv = __ldg(x + i);
-      if (!(fmaf(xv.x, sc.x, sh.x) > 0.f)) r.x = 0.f;
-      if (!(fmaf(xv.y, sc.y, sh.y) > 0.f)) r.y = 0.f;
-      if (!(fmaf(xv.z, sc.z, sh.z) > 0.f)) r.z = 0.f;
-      if (!(fmaf(xv.w, sc.w, sh.w) > 0.f)) r.w = 0.f;
+      if (!(fmaf(xv.x - mu.x, sc.x, sh.x) > 0.f)) r.x = 0.f;
+      if (!(fmaf(xv.y - mu.y, sc.y, sh.y) > 0.f)) r.y = 0.f;
+      if (!(fmaf(xv.z - mu.z, sc.z, sh.z) > 0.f)) r.z = 0.f;
+      if (!(fmaf(xv.w - mu.w, sc.w, sh.w) > 0.f)) r.w = 0.f;
     }
     if (accumulate) {
       const float4 p = dx[i];
@@ -525,13 +532,24 @@ int bn_finalize(const float* mean, const float* var_biased, const float* gamma, 
   return FPD_OK;
 }
 
-int affine_act_split(const float* x, const float* scale, const float* shift, int relu, float* a_hi, float* a_lo,
-                     int64_t P, int C, cudaStream_t stream) {
+int affine_act_split(const float* x, const float* mean, const float* scale, const float* shift, int relu,
+                     float* a_hi, float* a_lo, int64_t P, int C, cudaStream_t stream) {
   FPD_REQUIRE(C % 4 == 0, "affine_act_split: C=%d must be a multiple of 4", C);
   FPD_REQUIRE((scale == nullptr) == (shift == nullptr), "affine_act_split: scale/shift must come in pairs");
   const int64_t n4 = P * C / 4;
-  affine_act_split_kernel<<<grid_for(n4, 256), 256, 0, stream>>>((const float4*)x, scale, shift, relu, (float4*)a_hi,
-                                                                 (float4*)a_lo, n4, C / 4);
+  affine_act_split_kernel<<<grid_for(n4, 256), 256, 0, stream>>>((const float4*)x, mean, scale, shift, relu,
+                                                                 (float4*)a_hi, (float4*)a_lo, n4, C / 4, 1);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int affine_act(const float* x, const float* mean, const float* scale, const float* shift, int relu, float* y,
+               int64_t P, int C, cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0, "affine_act: C=%d must be a multiple of 4", C);
+  FPD_REQUIRE((scale == nullptr) == (shift == nullptr), "affine_act: scale/shift must come in pairs");
+  const int64_t n4 = P * C / 4;
+  affine_act_split_kernel<<<grid_for(n4, 256), 256, 0, stream>>>((const float4*)x, mean, scale, shift, relu,
+                                                                 (float4*)y, nullptr, n4, C / 4, 0);
   FPD_LAUNCH_CHECK();
   return FPD_OK;
 }
@@ -647,12 +665,12 @@ int bn_bwd_apply(const float* da, const float* x, const float* mean, const float
   return FPD_OK;
 }
 
-int affine_act_bwd(const float* da, const float* x, const float* scale, const float* shift, int relu,
-                   int accumulate, float* dx, int64_t P, int C, cudaStream_t stream) {
+int affine_act_bwd(const float* da, const float* x, const float* mean, const float* scale, const float* shift,
+                   int relu, int accumulate, float* dx, int64_t P, int C, cudaStream_t stream) {
   FPD_REQUIRE(C % 4 == 0, "affine_act_bwd: C=%d must be a multiple of 4", C);
   const int64_t n4 = P * C / 4;
-  affine_act_bwd_kernel<<<grid_for(n4, 256), 256, 0, stream>>>((const float4*)da, (const float4*)x, scale, shift,
-                                                               relu, accumulate, (float4*)dx, n4, C / 4);
+  affine_act_bwd_kernel<<<grid_for(n4, 256), 256, 0, stream>>>((const float4*)da, (const float4*)x, mean, scale,
+                                                               shift, relu, accumulate, (float4*)dx, n4, C / 4);
   FPD_LAUNCH_CHECK();
   return FPD_OK;
 }

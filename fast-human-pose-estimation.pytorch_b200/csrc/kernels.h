@@ -35,13 +35,16 @@ int conv_simt_wgrad(const float* x, const float* dy, float* dw_oihw, float scale
 size_t bn_stats_workspace_bytes(int64_t P, int C);
 int bn_stats(const float* x, int64_t P, int C, float* mean, float* var_biased, void* workspace, size_t ws_bytes,
              cudaStream_t stream);
-// scale = gamma*rsqrt(var+eps), shift = beta - mean*scale ; optional running-stat update (momentum, unbiased var)
+// centred affine y = (x-mean)*scale + shift: scale = gamma*rsqrt(var+eps), shift = beta ; optional running-stat update (momentum, unbiased var)
 int bn_finalize(const float* mean, const float* var_biased, const float* gamma, const float* beta, float eps,
                 int64_t count, float* scale, float* shift, float* invstd, float* running_mean, float* running_var,
                 float momentum, int C, cudaStream_t stream);
-// a = act(x*scale+shift) (scale/shift may be null = identity; relu optional); hi = tf32(a), lo = tf32(a-hi)
-int affine_act_split(const float* x, const float* scale, const float* shift, int relu, float* a_hi, float* a_lo,
-                     int64_t P, int C, cudaStream_t stream);
+// a = act((x-mean)*scale+shift) (mean/scale/shift may be null = identity; relu optional); hi = tf32(a), lo = tf32(a-hi)
+int affine_act_split(const float* x, const float* mean, const float* scale, const float* shift, int relu,
+                     float* a_hi, float* a_lo, int64_t P, int C, cudaStream_t stream);
+// y = act(x*scale+shift), full fp32 (no operand rounding)
+int affine_act(const float* x, const float* mean, const float* scale, const float* shift, int relu, float* y,
+               int64_t P, int C, cudaStream_t stream);
 int maxpool2x2_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream);
 int maxpool2x2_bwd(const float* x, const float* dy, float* dx, int accumulate, int B, int H, int W, int C,
                    cudaStream_t stream);
@@ -65,8 +68,8 @@ int bn_bwd_apply(const float* da, const float* x, const float* mean, const float
                  const float* shift, const float* gamma, int relu, const float* sums, int accumulate, float* dx,
                  int64_t P, int C, cudaStream_t stream);
 // eval-mode / no-stat variant: dx (=|+=) da * mask * scale
-int affine_act_bwd(const float* da, const float* x, const float* scale, const float* shift, int relu,
-                   int accumulate, float* dx, int64_t P, int C, cudaStream_t stream);
+int affine_act_bwd(const float* da, const float* x, const float* mean, const float* scale, const float* shift,
+                   int relu, int accumulate, float* dx, int64_t P, int C, cudaStream_t stream);
 // OIHW fp32 -> [tap][O][I] (fwd) or [flipped tap][I][O] (dgrad), split into tf32 hi/lo
 int weight_prep(const float* w_oihw, float* w_hi, float* w_lo, int O, int I, int k, int for_dgrad,
                 cudaStream_t stream);

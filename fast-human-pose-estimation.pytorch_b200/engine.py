@@ -1,0 +1,367 @@
+"""Host-side execution engine for the stacked-hourglass hot path.
+
+The network topology is the reference's (lib/models/hourglass.py:32-52 Bottleneck.forward, :80-95
+Hourglass._hour_glass_forward, :170-192 HourglassNet.forward); the execution is not: activations live in
+NHWC, every op is a libfpd_b200 kernel (tcgen05 implicit-GEMM convs, fused BN/ReLU/operand-split, ...),
+and the backward pass is an explicit tape of kernel launches instead of a per-op autograd graph.
+
+Python here only sequences launches and owns tensors (torch = device memory + streams); there is no
+torch math on the hot path and no CPU fallback.
+"""
+import os
+
+import torch
+
+from . import ops
+
+
+def precision_passes():
+    """3 = 3xTF32 (fp32-grade, the parity mode and the default), 1 = single-pass TF32."""
+    mode = os.environ.get("FPD_PRECISION", "tf32x3").lower()
+    if mode in ("tf32x3", "3xtf32", "fp32"):
+        return 3
+    if mode in ("tf32", "tf32x1"):
+        return 1
+    raise ValueError("FPD_PRECISION must be tf32x3 or tf32, got %r" % mode)
+
+
+class Var:
+    """An activation tensor (NHWC) plus its gradient slot and cached batch statistics."""
+    __slots__ = ("data", "grad", "owned", "stats")
+
+    def __init__(self, data):
+        self.data = data
+        self.grad = None
+        self.owned = False   # True if self.grad may be modified in place
+        self.stats = None    # (mean, var) of data over pixels, shared by every BN that consumes it
+
+    def add_grad(self, g, owned):
+        if self.grad is None:
+            self.grad, self.owned = g, owned
+        elif self.owned:
+            ops.add(self.grad, g, out=self.grad)
+        else:
+            self.grad = ops.add(self.grad, g)
+            self.owned = True
+
+    def accum_target(self):
+        """Buffer a kernel may accumulate into (or None -> kernel should write a fresh tensor)."""
+        return self.grad if (self.grad is not None and self.owned) else None
+
+    def set_or_merge(self, dx, accumulated):
+        if accumulated:
+            return
+        self.add_grad(dx, True)
+
+
+class ConvRef:
+    __slots__ = ("name", "weight", "bias", "k", "stride", "pad", "cin", "cout")
+
+    def __init__(self, name, mod):
+        self.name = name
+        self.weight = mod.weight
+        self.bias = mod.bias
+        self.k = mod.kernel_size[0]
+        self.stride = mod.stride[0]
+        self.pad = mod.padding[0]
+        self.cin = mod.in_channels
+        self.cout = mod.out_channels
+
+    @property
+    def tc_fwd(self):
+        return self.stride == 1 and self.pad == self.k // 2 and ops.conv2d_tc_supported(self.cin, self.cout, self.k)
+
+    @property
+    def tc_dgrad(self):
+        return self.stride == 1 and self.pad == self.k // 2 and ops.conv2d_tc_supported(self.cout, self.cin, self.k)
+
+    @property
+    def tc_wgrad(self):
+        return self.stride == 1 and self.pad == self.k // 2 and ops.conv2d_wgrad_tc_supported(self.cin, self.cout,
+                                                                                               self.k)
+
+
+class BNRef:
+    __slots__ = ("name", "mod")
+
+    def __init__(self, name, mod):
+        self.name = name
+        self.mod = mod
+
+
+class PreparedWeights:
+    """Tensor-core operand forms of every conv weight: [tap][O][I] hi/lo (+ flipped/transposed for dgrad)."""
+
+    def __init__(self, convs, passes, need_dgrad):
+        self.fwd = {}
+        self.dgrad = {}
+        split = passes == 3
+        for c in convs:
+            w = c.weight.detach()
+            if c.tc_fwd:
+                self.fwd[c.name] = ops.weight_prep(w, for_dgrad=False, split=split)
+            if need_dgrad and c.tc_dgrad:
+                self.dgrad[c.name] = ops.weight_prep(w, for_dgrad=True, split=split)
+
+
+class Engine:
+    """Runs one forward (and optionally records a backward tape) of a hourglass-family module tree."""
+
+    def __init__(self, net):
+        self.net = net
+        self.convs = {}
+        self.bns = {}
+        for name, m in net.named_modules():
+            if isinstance(m, torch.nn.Conv2d):
+                self.convs[name] = ConvRef(name, m)
+            elif isinstance(m, torch.nn.BatchNorm2d):
+                self.bns[name] = BNRef(name, m)
+        self._eval_cache = None
+        self._eval_cache_key = None
+
+    # ------------------------------------------------------------------ parameter preparation
+    def _param_version(self):
+        v = 0
+        for p in self.net.parameters():
+            v += p._version
+        for b in self.net.buffers():
+            v += b._version
+        return (v, next(self.net.parameters()).device, precision_passes())
+
+    def _eval_prepared(self):
+        key = self._param_version()
+        if self._eval_cache is None or self._eval_cache_key != key:
+            passes = precision_passes()
+            w = PreparedWeights(self.convs.values(), passes, need_dgrad=False)
+            affine = {}
+            for name, b in self.bns.items():
+                m = b.mod
+                scale, shift, invstd = ops.bn_finalize(m.running_mean, m.running_var, m.weight.detach(),
+                                                       m.bias.detach(), m.eps, 1, None, None, 0.0)
+                affine[name] = (scale, shift, m.running_mean, invstd)
+            self._eval_cache = (w, affine)
+            self._eval_cache_key = key
+        return self._eval_cache
+
+    # ------------------------------------------------------------------ building blocks
+    def _bn_affine(self, ctx, x, bn_name):
+        """Returns (scale, shift, mean, invstd, batch) for y = (x-mean)*scale+shift; batch=False in eval mode
+        (mean/invstd then come from the running statistics)."""
+        b = self.bns[bn_name]
+        m = b.mod
+        if ctx.training:
+            if x.stats is None:
+                x.stats = ops.bn_stats(x.data)
+            mean, var = x.stats
+            count = x.data.numel() // x.data.shape[-1]
+            momentum = m.momentum if m.momentum is not None else 0.1
+            track = m.track_running_stats and m.running_mean is not None
+            scale, shift, invstd = ops.bn_finalize(mean, var, m.weight.detach(), m.bias.detach(), m.eps, count,
+                                                   m.running_mean if track else None,
+                                                   m.running_var if track else None, momentum)
+            if track and m.num_batches_tracked is not None:
+                ctx.nbt.append(m.num_batches_tracked)
+            return scale, shift, mean, invstd, True
+        scale, shift, rmean, rinvstd = ctx.affine[bn_name]
+        return scale, shift, rmean, rinvstd, False
+
+    def _bn_backward(self, ctx, x, bn_name, relu, da, aff):
+        """dL/d(act(bn(x))) = da  ->  accumulates dL/dx into x.grad and records dgamma/dbeta."""
+        m = self.bns[bn_name].mod
+        scale, shift, mean, invstd, batch = aff
+        tgt = x.accum_target()
+        if batch:
+            dx, dgamma, dbeta = ops.bn_bwd(da, x.data, mean, invstd, scale, shift, m.weight.detach(), relu,
+                                           accumulate_into=tgt)
+            ctx.pgrads[m.weight] = dgamma
+            ctx.pgrads[m.bias] = dbeta
+        else:  # eval-mode affine: statistics are constants, so no batch-statistics terms in dx
+            sums = ops.bn_bwd_reduce(da, x.data, mean, invstd, scale, shift, relu)
+            C = x.data.shape[-1]
+            ctx.pgrads[m.weight] = sums[C:]
+            ctx.pgrads[m.bias] = sums[:C]
+            dx = ops.affine_act_bwd(da, x.data, scale, shift, relu, accumulate_into=tgt, mean=mean)
+        x.set_or_merge(dx, tgt is not None)
+
+    def bn_act(self, ctx, x, bn_name, relu=True):
+        """Materialised y = relu(bn(x)) (stem bn1, fc bn): reference hourglass.py:117-119,161-168."""
+        aff = self._bn_affine(ctx, x, bn_name)
+        out = Var(ops.affine_act(x.data, aff[0], aff[1], relu, mean=aff[2]))
+        if ctx.tape is not None:
+            def bwd():
+                if out.grad is None:
+                    return
+                self._bn_backward(ctx, x, bn_name, relu, out.grad, aff)
+            ctx.tape.append(bwd)
+        return out
+
+    def conv(self, ctx, x, conv_name, bn_name=None, relu=False, residual=None, need_dx=True):
+        """y = conv(act(bn(x))) + bias (+ residual).  bn_name None -> the conv consumes x raw."""
+        c = self.convs[conv_name]
+        split = ctx.passes == 3
+        scale = shift = mean = None
+        aff = None
+        if bn_name is not None:
+            aff = self._bn_affine(ctx, x, bn_name)
+            scale, shift, mean = aff[0], aff[1], aff[2]
+        bias = c.bias.detach() if c.bias is not None else None
+        res = residual.data if residual is not None else None
+        a_hi = a_lo = None
+        if c.tc_fwd:
+            a_hi, a_lo = ops.affine_act_split(x.data, scale, shift, relu, split=split, mean=mean)
+            w_hi, w_lo = ctx.weights.fwd[conv_name]
+            y = ops.conv2d_tc(a_hi, a_lo, w_hi, w_lo, c.k, bias=bias, residual=res)
+        else:
+            a = ops.affine_act(x.data, scale, shift, relu, mean=mean) if bn_name is not None else x.data
+            y = ops.conv2d_simt_fwd(a, c.weight.detach(), bias=bias, residual=res, stride=c.stride, pad=c.pad)
+        out = Var(y)
+        if ctx.tape is not None:
+            keep_hi, keep_lo = (a_hi, a_lo) if c.tc_wgrad else (None, None)
+
+            def bwd():
+                dy = out.grad
+                if dy is None:
+                    return
+                if residual is not None:
+                    residual.add_grad(dy, owned=False)
+                if c.bias is not None:
+                    ctx.pgrads[c.bias] = ops.channel_sum(dy)
+                dy_hi = dy_lo = None
+                if c.tc_wgrad or (need_dx and c.tc_dgrad):
+                    dy_hi, dy_lo = ops.affine_act_split(dy, split=split)
+                # ---- weight gradient
+                if c.tc_wgrad:
+                    ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc(keep_hi, keep_lo, dy_hi, dy_lo, c.k)
+                else:
+                    a_full = (ops.affine_act(x.data, scale, shift, relu, mean=mean) if bn_name is not None
+                              else x.data)
+                    ctx.pgrads[c.weight] = ops.conv2d_simt_wgrad(a_full, dy, c.k, stride=c.stride, pad=c.pad)
+                if not need_dx:
+                    return
+                # ---- data gradient w.r.t. the conv input a = act(bn(x))
+                if c.tc_dgrad:
+                    wd_hi, wd_lo = ctx.weights.dgrad[conv_name]
+                    da = ops.conv2d_tc(dy_hi, dy_lo, wd_hi, wd_lo, c.k)
+                else:
+                    da = ops.conv2d_simt_dgrad(dy, c.weight.detach(), x.data.shape[1:3], stride=c.stride, pad=c.pad)
+                if bn_name is not None:
+                    self._bn_backward(ctx, x, bn_name, relu, da, aff)
+                else:
+                    x.add_grad(da, owned=True)
+            ctx.tape.append(bwd)
+        return out
+
+    def maxpool(self, ctx, x):
+        out = Var(ops.maxpool2x2(x.data))
+        if ctx.tape is not None:
+            def bwd():
+                if out.grad is None:
+                    return
+                tgt = x.accum_target()
+                dx = ops.maxpool2x2_bwd(x.data, out.grad, accumulate_into=tgt)
+                x.set_or_merge(dx, tgt is not None)
+            ctx.tape.append(bwd)
+        return out
+
+    def upsample_add(self, ctx, up1, low):
+        out = Var(ops.upsample2x_add(up1.data, low.data))
+        if ctx.tape is not None:
+            def bwd():
+                if out.grad is None:
+                    return
+                up1.add_grad(out.grad, owned=False)
+                low.add_grad(ops.upsample2x_bwd(out.grad), owned=True)
+            ctx.tape.append(bwd)
+        return out
+
+    # ------------------------------------------------------------------ hourglass topology
+    def bottleneck(self, ctx, x, prefix):
+        """Pre-activation residual block, reference hourglass.py:32-52."""
+        has_ds = (prefix + ".downsample.0") in self.convs
+        skip = self.conv(ctx, x, prefix + ".downsample.0") if has_ds else x
+        y = self.conv(ctx, x, prefix + ".conv1", prefix + ".bn1", relu=True)
+        y = self.conv(ctx, y, prefix + ".conv2", prefix + ".bn2", relu=True)
+        return self.conv(ctx, y, prefix + ".conv3", prefix + ".bn3", relu=True, residual=skip)
+
+    def residual_seq(self, ctx, x, prefix, nblocks):
+        for i in range(nblocks):
+            x = self.bottleneck(ctx, x, "%s.%d" % (prefix, i))
+        return x
+
+    def hourglass(self, ctx, n, x, prefix, nblocks):
+        """Recursive U, reference hourglass.py:80-92."""
+        up1 = self.residual_seq(ctx, x, "%s.%d.0" % (prefix, n - 1), nblocks)
+        low1 = self.maxpool(ctx, x)
+        low1 = self.residual_seq(ctx, low1, "%s.%d.1" % (prefix, n - 1), nblocks)
+        if n > 1:
+            low2 = self.hourglass(ctx, n - 1, low1, prefix, nblocks)
+        else:
+            low2 = self.residual_seq(ctx, low1, "%s.%d.3" % (prefix, n - 1), nblocks)
+        low3 = self.residual_seq(ctx, low2, "%s.%d.2" % (prefix, n - 1), nblocks)
+        return self.upsample_add(ctx, up1, low3)
+
+    def hourglass_net(self, ctx, img_nchw):
+        """HourglassNet.forward, reference hourglass.py:170-192. Returns the per-stack heat-map Vars (NHWC)."""
+        net = self.net
+        nb = net.num_blocks
+        x = Var(ops.nchw_to_nhwc(img_nchw))
+        x = self.conv(ctx, x, "conv1", need_dx=False)
+        x = self.bn_act(ctx, x, "bn1", relu=True)
+        x = self.residual_seq(ctx, x, "layer1", 1)
+        x = self.maxpool(ctx, x)
+        x = self.residual_seq(ctx, x, "layer2", 1)
+        x = self.residual_seq(ctx, x, "layer3", 1)
+        outs = []
+        for i in range(net.num_stacks):
+            y = self.hourglass(ctx, 4, x, "hg.%d.hg" % i, nb)
+            y = self.residual_seq(ctx, y, "res.%d" % i, nb)
+            y = self.conv(ctx, y, "fc.%d.0" % i)
+            y = self.bn_act(ctx, y, "fc.%d.1" % i, relu=True)
+            score = self.conv(ctx, y, "score.%d" % i)
+            outs.append(score)
+            if i < net.num_stacks - 1:
+                t = self.conv(ctx, y, "fc_.%d" % i, residual=x)
+                x = self.conv(ctx, score, "score_.%d" % i, residual=t)
+        return outs
+
+    # ------------------------------------------------------------------ entry points
+    def forward(self, img_nchw, training, record_tape):
+        ctx = _Ctx()
+        ctx.training = training
+        ctx.passes = precision_passes()
+        ctx.tape = [] if record_tape else None
+        if training:
+            ctx.weights = PreparedWeights(self.convs.values(), ctx.passes, need_dgrad=record_tape)
+            ctx.affine = None
+        else:
+            w, affine = self._eval_prepared()
+            if record_tape:
+                w = PreparedWeights(self.convs.values(), ctx.passes, need_dgrad=True)
+            ctx.weights, ctx.affine = w, affine
+        outs = self.hourglass_net(ctx, img_nchw.contiguous().float())
+        if ctx.nbt:
+            torch._foreach_add_(ctx.nbt, 1)
+        ctx.outs = outs
+        return ctx
+
+    def backward(self, ctx, out_grads_nhwc):
+        """out_grads_nhwc: list (per stack) of NHWC gradient tensors or None. Returns {param: grad}."""
+        for v, g in zip(ctx.outs, out_grads_nhwc):
+            if g is not None:
+                v.add_grad(g, owned=False)
+        for fn in reversed(ctx.tape):
+            fn()
+        ctx.tape = None
+        return ctx.pgrads
+
+
+class _Ctx:
+    def __init__(self):
+        self.training = False
+        self.passes = 3
+        self.tape = None
+        self.weights = None
+        self.affine = None
+        self.pgrads = {}
+        self.nbt = []
+        self.outs = None

@@ -1,0 +1,2 @@
+# same registry the reference builds in lib/models/__init__.py:15-17 (looked up by cfg.MODEL.NAME)
+from . import hourglass  # noqa: F401

@@ -56,15 +56,26 @@ def weight_prep(w_oihw, for_dgrad=False, split=True):
     return hi, lo
 
 
-def affine_act_split(x, scale=None, shift=None, relu=False, split=True, out_hi=None, out_lo=None):
+def affine_act_split(x, scale=None, shift=None, relu=False, split=True, out_hi=None, out_lo=None, mean=None):
     _chk(x, "x")
     C = x.shape[-1]
     P = x.numel() // C
     hi = out_hi if out_hi is not None else torch.empty_like(x)
     lo = (out_lo if out_lo is not None else torch.empty_like(x)) if split else None
-    N.check(N.lib().fpd_affine_act_split(_p(x), _p(scale), _p(shift), int(relu), _p(hi), _p(lo), P, C, _stream()),
+    N.check(N.lib().fpd_affine_act_split(_p(x), _p(mean), _p(scale), _p(shift), int(relu), _p(hi), _p(lo), P, C,
+                                         _stream()),
             "affine_act_split")
     return hi, lo
+
+
+def affine_act(x, scale=None, shift=None, relu=False, out=None, mean=None):
+    _chk(x, "x")
+    C = x.shape[-1]
+    P = x.numel() // C
+    y = out if out is not None else torch.empty_like(x)
+    N.check(N.lib().fpd_affine_act(_p(x), _p(mean), _p(scale), _p(shift), int(relu), _p(y), P, C, _stream()),
+            "affine_act")
+    return y
 
 
 def conv2d_tc(a_hi, a_lo, w_hi, w_lo, ksize, bias=None, residual=None, relu_mask=None, out=None, out_scale=1.0):
@@ -151,14 +162,22 @@ def channel_sum(dy, scale=1.0):
     return out
 
 
-def bn_bwd(da, x, mean, invstd, scale, shift, gamma, relu, accumulate_into=None):
-    """Returns (dx, dgamma, dbeta) for y = relu?(bn(x)) given da = dL/dy."""
+def bn_bwd_reduce(da, x, mean, invstd, scale, shift, relu):
+    """sums[0:C] = sum dz (= dbeta), sums[C:2C] = sum dz*xhat (= dgamma), dz = da masked by the ReLU."""
     C = x.shape[-1]
     P = x.numel() // C
     sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
     ws = _ws.get(N.lib().fpd_channel_reduce_workspace_bytes(P, C), x.device)
     N.check(N.lib().fpd_bn_bwd_reduce(_p(da), _p(x), _p(mean), _p(invstd), _p(scale), _p(shift), int(relu), P, C,
                                       _p(sums), _p(ws), ws.numel(), _stream()), "bn_bwd_reduce")
+    return sums
+
+
+def bn_bwd(da, x, mean, invstd, scale, shift, gamma, relu, accumulate_into=None):
+    """Returns (dx, dgamma, dbeta) for y = relu?(bn(x)) given da = dL/dy (train-mode batch statistics)."""
+    C = x.shape[-1]
+    P = x.numel() // C
+    sums = bn_bwd_reduce(da, x, mean, invstd, scale, shift, relu)
     dx = accumulate_into if accumulate_into is not None else torch.empty_like(x)
     N.check(N.lib().fpd_bn_bwd_apply(_p(da), _p(x), _p(mean), _p(invstd), _p(scale), _p(shift), _p(gamma), int(relu),
                                      _p(sums), int(accumulate_into is not None), _p(dx), P, C, _stream()),
@@ -166,11 +185,11 @@ def bn_bwd(da, x, mean, invstd, scale, shift, gamma, relu, accumulate_into=None)
     return dx, sums[C:], sums[:C]
 
 
-def affine_act_bwd(da, x, scale, shift, relu, accumulate_into=None):
+def affine_act_bwd(da, x, scale, shift, relu, accumulate_into=None, mean=None):
     C = x.shape[-1]
     P = x.numel() // C
     dx = accumulate_into if accumulate_into is not None else torch.empty_like(x)
-    N.check(N.lib().fpd_affine_act_bwd(_p(da), _p(x), _p(scale), _p(shift), int(relu),
+    N.check(N.lib().fpd_affine_act_bwd(_p(da), _p(x), _p(mean), _p(scale), _p(shift), int(relu),
                                        int(accumulate_into is not None), _p(dx), P, C, _stream()), "affine_act_bwd")
     return dx
 

@@ -87,14 +87,20 @@ size_t fpd_bn_stats_workspace_bytes(int64_t P, int C);
 /* per-channel batch mean and biased variance of x[P,C] */
 int fpd_bn_stats(const float* x, int64_t P, int C, float* mean, float* var_biased, void* workspace,
                  size_t workspace_bytes, fpd_stream_t stream);
-/* scale = gamma/sqrt(var+eps), shift = beta - mean*scale, invstd (optional); running stats (optional,
- * both or neither) updated with `momentum` and the unbiased variance like nn.BatchNorm2d. */
+/* Centred affine form used by every consumer: y = (x - mean) * scale + shift with
+ * scale = gamma/sqrt(var+eps), shift = beta (no cancellation when |mean| >> std); invstd optional;
+ * running stats (optional, both or neither) updated with `momentum` and the unbiased variance like
+ * nn.BatchNorm2d. */
 int fpd_bn_finalize(const float* mean, const float* var_biased, const float* gamma, const float* beta, float eps,
                     int64_t count, float* scale, float* shift, float* invstd, float* running_mean,
                     float* running_var, float momentum, int C, fpd_stream_t stream);
-/* a = relu?(x*scale+shift) (scale/shift NULL = identity) -> a_hi = tf32(a), a_lo = tf32(a - a_hi) (optional) */
-int fpd_affine_act_split(const float* x, const float* scale, const float* shift, int relu, float* a_hi,
-                         float* a_lo, int64_t P, int C, fpd_stream_t stream);
+/* a = relu?((x-mean)*scale+shift) (scale/shift NULL = identity, mean NULL = 0)
+ * -> a_hi = tf32(a), a_lo = tf32(a - a_hi) (optional) */
+int fpd_affine_act_split(const float* x, const float* mean, const float* scale, const float* shift, int relu,
+                         float* a_hi, float* a_lo, int64_t P, int C, fpd_stream_t stream);
+/* y = relu?((x-mean)*scale+shift) in full fp32 (materialised activations: stem output, fc output) */
+int fpd_affine_act(const float* x, const float* mean, const float* scale, const float* shift, int relu, float* y,
+                   int64_t P, int C, fpd_stream_t stream);
 size_t fpd_channel_reduce_workspace_bytes(int64_t P, int C);
 int fpd_channel_sum(const float* dy, int64_t P, int C, float scale, float* out, void* workspace,
                     size_t workspace_bytes, fpd_stream_t stream);
@@ -106,8 +112,8 @@ int fpd_bn_bwd_reduce(const float* da, const float* x, const float* mean, const 
 int fpd_bn_bwd_apply(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
                      const float* shift, const float* gamma, int relu, const float* sums, int accumulate, float* dx,
                      int64_t P, int C, fpd_stream_t stream);
-int fpd_affine_act_bwd(const float* da, const float* x, const float* scale, const float* shift, int relu,
-                       int accumulate, float* dx, int64_t P, int C, fpd_stream_t stream);
+int fpd_affine_act_bwd(const float* da, const float* x, const float* mean, const float* scale, const float* shift,
+                       int relu, int accumulate, float* dx, int64_t P, int C, fpd_stream_t stream);
 int fpd_maxpool2x2_fwd(const float* x, float* y, int B, int H, int W, int C, fpd_stream_t stream);
 int fpd_maxpool2x2_bwd(const float* x, const float* dy, float* dx, int accumulate, int B, int H, int W, int C,
                        fpd_stream_t stream);

@@ -1,0 +1,171 @@
+"""Generate the golden vectors under tests/golden/ by running the REAL reference
+(/root/reference, read-only) on seeded synthetic inputs. Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The reference has no tests / fixtures of its own, so these vectors -- outputs of its
+own lib/models/hourglass.py, lib/core/loss.py, lib/core/inference.py, lib/utils/transforms.py and
+lib/nms/nms.py -- are what pins the oracle (tests/test_oracle.py) and, through it, the CUDA path.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+NS = types.SimpleNamespace
+
+
+def load(name, rel):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def cfg(f, s, j=16):
+    return NS(MODEL=NS(EXTRA=NS(NUM_FEATURES=f, NUM_STACKS=s, NUM_BLOCKS=1), NUM_JOINTS=j))
+
+
+def gaussian_targets(rng, B, J, h, w):
+    """Reference-style targets (lib/dataset/JointsDataset.py:251-284): sigma=2, 13x13 patch, peak 1."""
+    t = np.zeros((B, J, h, w), np.float32)
+    size = 13
+    xs = np.arange(size, dtype=np.float32)
+    g = np.exp(-((xs[None] - 6) ** 2 + (xs[:, None] - 6) ** 2) / (2 * 2.0 ** 2))
+    for b in range(B):
+        for j in range(J):
+            mx, my = rng.randint(0, w), rng.randint(0, h)
+            ul = (mx - 6, my - 6)
+            gx = (max(0, -ul[0]), min(ul[0] + size, w) - ul[0])
+            gy = (max(0, -ul[1]), min(ul[1] + size, h) - ul[1])
+            ix = (max(0, ul[0]), min(ul[0] + size, w))
+            iy = (max(0, ul[1]), min(ul[1] + size, h))
+            t[b, j, iy[0]:iy[1], ix[0]:ix[1]] = g[gy[0]:gy[1], gx[0]:gx[1]]
+    return t
+
+
+def main():
+    torch.set_num_threads(4)
+    hg = load("ref_hourglass", "lib/models/hourglass.py")
+    loss_mod = load("ref_loss", "lib/core/loss.py")
+    sys.path.insert(0, os.path.join(REF, "lib"))
+    from core.inference import get_max_preds           # noqa: E402
+    from utils.transforms import flip_back             # noqa: E402
+    # nms.py imports two Cython extensions that are not built here; stub them (pure-numpy `nms` is what we use)
+    sys.modules.setdefault("cpu_nms", types.SimpleNamespace(cpu_nms=None))
+    sys.modules.setdefault("gpu_nms", types.SimpleNamespace(gpu_nms=None))
+    src = open(os.path.join(REF, "lib/nms/nms.py")).read().replace("from .cpu_nms import cpu_nms", "").replace(
+        "from .gpu_nms import gpu_nms", "")
+    nms_ns = {}
+    exec(compile(src, "ref_nms.py", "exec"), nms_ns)
+
+    rng = np.random.RandomState(0)
+    B, H, W, J = 2, 64, 64, 16
+    h, w = H // 4, W // 4
+
+    # ---- 1. hourglass s=2 f=64, train mode, plain MSE (function.train semantics, function.py:44-63) ----
+    torch.manual_seed(0)
+    net = hg.get_pose_net(cfg(64, 2), True)
+    net.train()
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    x = torch.randn(B, 3, H, W)
+    target = torch.from_numpy(gaussian_targets(rng, B, J, h, w))
+    tw = torch.from_numpy((rng.rand(B, J, 1) > 0.2).astype(np.float32))
+    crit = loss_mod.JointsMSELoss(use_target_weight=True)
+    outs = net(x)
+    loss = crit(outs[0], target, tw)
+    for o in outs[1:]:
+        loss = loss + crit(o, target, tw)
+    net.zero_grad()
+    loss.backward()
+    sd1 = net.state_dict()
+    save = {"x": x.numpy(), "target": target.numpy(), "target_weight": tw.numpy(), "loss": np.float32(loss.item())}
+    for i, o in enumerate(outs):
+        save["out%d" % i] = o.detach().numpy()
+    for k, v in sd0.items():
+        save["sd/" + k] = v.numpy()
+    for k, p in net.named_parameters():
+        save["grad/" + k] = p.grad.numpy()
+    for k in ("bn1.running_mean", "bn1.running_var", "hg.1.hg.0.3.0.bn2.running_mean", "fc.1.1.running_var",
+              "bn1.num_batches_tracked"):
+        save["after/" + k] = sd1[k].numpy()
+    np.savez_compressed(os.path.join(OUT, "hg_s2f64_train.npz"), **save)
+
+    # ---- 2. FPD: same student, frozen teacher s=1 f=64 in eval mode (function.py:119-134), alpha=0.5 ----
+    torch.manual_seed(1)
+    tnet = hg.get_pose_net(cfg(64, 1), False)
+    # give the teacher non-trivial running statistics
+    for m in tnet.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+    tnet.eval()
+    net.load_state_dict(sd0)
+    net.train()
+    net.zero_grad()
+    outs = net(x)
+    with torch.no_grad():
+        tout = tnet(x)[-1]
+    pose = crit(outs[0], target, tw)
+    kd = crit(outs[0], tout, tw)
+    for o in outs[1:]:
+        pose = pose + crit(o, target, tw)
+        kd = kd + crit(o, tout, tw)
+    alpha = 0.5
+    total = (1 - alpha) * pose + alpha * kd
+    total.backward()
+    save = {"alpha": np.float32(alpha), "pose": np.float32(pose.item()), "kd": np.float32(kd.item()),
+            "loss": np.float32(total.item()), "teacher_out": tout.numpy()}
+    for k, v in tnet.state_dict().items():
+        save["tsd/" + k] = v.numpy()
+    names, norms = [], []
+    for k, p in net.named_parameters():
+        names.append(k)
+        norms.append(float(p.grad.double().norm()))
+    save["grad_names"] = np.array(names)
+    save["grad_norms"] = np.array(norms, np.float64)
+    for k in ("conv1.weight", "layer2.0.conv2.weight", "hg.0.hg.0.3.0.conv2.weight", "hg.1.hg.3.0.0.bn1.weight",
+              "fc.0.0.weight", "score.1.bias", "score_.0.weight", "fc_.0.bias"):
+        save["grad/" + k] = dict(net.named_parameters())[k].grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "hg_fpd.npz"), **save)
+
+    # ---- 3. JointsMSELoss module on its own (loss.py:21-39) ----
+    o = torch.randn(3, J, 8, 8)
+    t = torch.rand(3, J, 8, 8)
+    w3 = torch.rand(3, J, 1)
+    np.savez_compressed(os.path.join(OUT, "loss.npz"), out=o.numpy(), target=t.numpy(), tw=w3.numpy(),
+                        with_w=np.float32(loss_mod.JointsMSELoss(True)(o, t, w3).item()),
+                        without_w=np.float32(loss_mod.JointsMSELoss(False)(o, t, w3).item()))
+
+    # ---- 4. decode: get_max_preds / flip_back (+shift, average as in function.py:224-240) / nms ----
+    hm = rng.randn(3, J, 16, 12).astype(np.float32)
+    hm[0, 0] = 0.5           # ties: first index wins
+    hm[0, 1] = -1.0          # max <= 0 -> preds zeroed
+    hf = rng.randn(3, J, 16, 12).astype(np.float32)
+    pairs = [[0, 5], [1, 4], [2, 3], [10, 15], [11, 14], [12, 13]]  # lib/dataset/mpii.py:32
+    preds, maxvals = get_max_preds(hm)
+    fb = flip_back(hf.copy(), pairs)
+    shifted = fb.copy()
+    shifted[:, :, :, 1:] = shifted.copy()[:, :, :, 0:-1]
+    merged = (hm + shifted) * np.float32(0.5)
+    mp, mv = get_max_preds(merged)
+    n = 300
+    x1 = rng.uniform(0, 200, n); y1 = rng.uniform(0, 200, n)
+    dets = np.stack([x1, y1, x1 + rng.uniform(8, 128, n), y1 + rng.uniform(8, 128, n), rng.uniform(0, 1, n)],
+                    1).astype(np.float32)
+    keep = np.array(nms_ns["nms"](dets, 0.6), np.int64)
+    np.savez_compressed(os.path.join(OUT, "decode.npz"), hm=hm, hm_flipped_raw=hf, flip_back=fb, merged=merged,
+                        preds=preds, maxvals=maxvals, merged_preds=mp, merged_maxvals=mv, dets=dets, nms_keep=keep,
+                        nms_thresh=np.float32(0.6))
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

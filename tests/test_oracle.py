@@ -1,0 +1,138 @@
+"""CPU suite (no GPU): pins the oracle (oracle/) against golden vectors produced by the real reference
+(tests/golden/make_golden.py) and -- when /root/reference exists -- against the live reference modules."""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode_oracle as D
+from oracle import hourglass_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REF = "/root/reference"
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLD, name), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def _sd(gold, prefix="sd/"):
+    return {k[len(prefix):]: torch.from_numpy(v.copy()) for k, v in gold.items() if k.startswith(prefix)}
+
+
+def _rel(a, b):
+    a = torch.as_tensor(a).double()
+    b = torch.as_tensor(b).double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def train_gold():
+    return _load("hg_s2f64_train.npz")
+
+
+def test_oracle_forward_loss_grads_match_reference_golden(train_gold):
+    torch.set_num_threads(4)
+    g = train_gold
+    sd = _sd(g)
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.dtype == torch.float32 and "running" not in k}
+    sd.update(params)
+    x = torch.from_numpy(g["x"])
+    outs = O.hourglass_net(sd, x, num_stacks=2, num_blocks=1, training=True)
+    for i, o in enumerate(outs):
+        assert _rel(o.detach(), g["out%d" % i]) < 2e-5
+    loss, pose, _ = O.fpd_loss(outs, torch.from_numpy(g["target"]), torch.from_numpy(g["target_weight"]))
+    assert abs(loss.item() - float(g["loss"])) < 1e-6 * abs(float(g["loss"]))
+    loss.backward()
+    worst = 0.0
+    for k, p in params.items():
+        worst = max(worst, _rel(p.grad, g["grad/" + k]))
+    assert worst < 2e-3, worst   # fp32 round-off through ~60 train-mode BN layers (see DESIGN.md on conditioning)
+    # running statistics are updated like nn.BatchNorm2d does
+    assert _rel(sd["bn1.running_mean"], g["after/bn1.running_mean"]) < 1e-6
+    assert _rel(sd["fc.1.1.running_var"], g["after/fc.1.1.running_var"]) < 1e-6
+
+
+def test_oracle_fpd_loss_matches_reference_golden(train_gold):
+    torch.set_num_threads(4)
+    g, f = train_gold, _load("hg_fpd.npz")
+    sd = _sd(g)
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.dtype == torch.float32 and "running" not in k}
+    sd.update(params)
+    tsd = _sd(f, "tsd/")
+    x = torch.from_numpy(g["x"])
+    with torch.no_grad():
+        tout = O.hourglass_net(tsd, x, num_stacks=1, training=False)[-1]
+    assert _rel(tout, f["teacher_out"]) < 1e-5
+    outs = O.hourglass_net(sd, x, num_stacks=2, training=True)
+    loss, pose, kd = O.fpd_loss(outs, torch.from_numpy(g["target"]), torch.from_numpy(g["target_weight"]), tout,
+                                float(f["alpha"]))
+    for got, key in ((pose, "pose"), (kd, "kd"), (loss, "loss")):
+        assert abs(got.item() - float(f[key])) < 2e-5 * abs(float(f[key])), key
+    loss.backward()
+    for k in [k[5:] for k in f if k.startswith("grad/")]:
+        assert _rel(params[k].grad, f["grad/" + k]) < 2e-3, k
+    norms = dict(zip(f["grad_names"].tolist(), f["grad_norms"].tolist()))
+    for k, p in params.items():
+        assert abs(p.grad.double().norm().item() - norms[k]) < 2e-3 * norms[k] + 1e-12, k
+
+
+def test_joints_mse_closed_form_matches_reference_golden():
+    g = _load("loss.npz")
+    o, t, w = (torch.from_numpy(g[k]) for k in ("out", "target", "tw"))
+    assert abs(O.joints_mse(o, t, w, True).item() - float(g["with_w"])) < 1e-6 * float(g["with_w"])
+    assert abs(O.joints_mse(o, t, w, False).item() - float(g["without_w"])) < 1e-6 * float(g["without_w"])
+
+
+def test_decode_and_nms_match_reference_golden():
+    g = _load("decode.npz")
+    preds, maxvals = D.get_max_preds(g["hm"])
+    assert np.array_equal(preds, g["preds"]) and np.array_equal(maxvals, g["maxvals"])
+    assert np.array_equal(D.flip_back(g["hm_flipped_raw"], D.MPII_FLIP_PAIRS), g["flip_back"])
+    merged = D.flip_test_merge(g["hm"], g["hm_flipped_raw"], D.MPII_FLIP_PAIRS, True)
+    assert np.array_equal(merged, g["merged"])
+    mp, mv = D.get_max_preds(merged)
+    assert np.array_equal(mp, g["merged_preds"]) and np.array_equal(mv, g["merged_maxvals"])
+    assert D.nms(g["dets"], float(g["nms_thresh"])) == g["nms_keep"].tolist()
+    assert D.nms(np.zeros((0, 5), np.float32), 0.5) == []
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="live reference only exists in the build container")
+def test_oracle_matches_live_reference_module():
+    torch.set_num_threads(4)
+    spec = importlib.util.spec_from_file_location("ref_hg_live", os.path.join(REF, "lib/models/hourglass.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    NS = types.SimpleNamespace
+    cfg = NS(MODEL=NS(EXTRA=NS(NUM_FEATURES=64, NUM_STACKS=1, NUM_BLOCKS=1), NUM_JOINTS=16))
+    torch.manual_seed(3)
+    net = m.get_pose_net(cfg, True)
+    x = torch.randn(2, 3, 64, 64)
+    for training in (True, False):
+        net.train(training)
+        sd = {k: v.clone() for k, v in net.state_dict().items()}
+        with torch.no_grad():
+            ref = net(x)
+            got = O.hourglass_net(sd, x, num_stacks=1, training=training)
+        assert _rel(got[0], ref[0]) < 1e-5
+
+
+def test_dropin_module_state_dict_matches_reference_keys(train_gold):
+    """Boundary: same state_dict keys/shapes as the reference => strict=True checkpoint loading."""
+    import fpd_b200  # noqa: F401
+    from fpd_b200.lib.models import hourglass as H
+    NS = types.SimpleNamespace
+    cfg = NS(MODEL=NS(EXTRA=NS(NUM_FEATURES=64, NUM_STACKS=2, NUM_BLOCKS=1), NUM_JOINTS=16))
+    net = H.get_pose_net(cfg, is_train=True)
+    gold_sd = _sd(train_gold)
+    own = net.state_dict()
+    assert list(own.keys()) == list(gold_sd.keys())
+    assert all(own[k].shape == gold_sd[k].shape for k in own)
+    net.load_state_dict(gold_sd, strict=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        net(torch.zeros(1, 3, 64, 64))
