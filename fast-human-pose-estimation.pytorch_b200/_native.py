@@ -22,6 +22,7 @@ _SIGNATURES = {
     "fpd_last_error": (c_char_p, []),
     "fpd_version": (c_int, []),
     "fpd_sm_count": (c_int, []),
+    "fpd_launch_count": (ctypes.c_longlong, []),
     "fpd_conv2d_tc_supported": (c_int, [c_int, c_int, c_int]),
     "fpd_conv2d_tc": (c_int, [P, P, P, P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "fpd_conv2d_wgrad_tc_supported": (c_int, [c_int, c_int, c_int]),

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 #include "../../include/fpd_b200.h"
@@ -13,6 +14,8 @@
 namespace fpd {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;
@@ -77,6 +80,7 @@ extern "C" {
 const char* fpd_last_error(void) { return fpd::g_err; }
 int fpd_version(void) { return 100; }
 int fpd_sm_count(void) { return device_sm_count(); }
+long long fpd_launch_count(void) { return fpd::g_launches.load(std::memory_order_relaxed); }
 
 int fpd_conv2d_tc_supported(int Cin, int Cout, int ksize) { return conv_tc_supported(Cin, Cout, ksize) ? 1 : 0; }
 

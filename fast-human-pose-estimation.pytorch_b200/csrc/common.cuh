@@ -35,7 +35,14 @@ void set_last_error(const char* fmt, ...);
     }                                                                                              \
   } while (0)
 
-#define FPD_LAUNCH_CHECK() FPD_CUDA_CHECK(cudaPeekAtLastError())
+// every kernel launch in the library is followed by exactly one FPD_LAUNCH_CHECK: it doubles as the launch counter
+// behind fpd_launch_count() (what bench.py reports as gpu_launches).
+void count_launch();
+#define FPD_LAUNCH_CHECK()                  \
+  do {                                      \
+    fpd::count_launch();                    \
+    FPD_CUDA_CHECK(cudaPeekAtLastError());  \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // numeric helpers

@@ -1,0 +1,152 @@
+"""One FPD training step as a replayable CUDA graph.
+
+What the reference does per iteration (lib/core/function.py:119-147 fpd_train): student forward, teacher
+forward, 2 x NUM_STACKS JointsMSELoss evaluations, backward (through student AND teacher), Adam -- ~20k
+eager ATen launches plus a DataParallel replicate/scatter/gather. Here the same update is:
+
+    graph replay { weight prep -> student fwd (tape) -> teacher fwd (eval, no tape) -> fused FPD loss+grad
+                   -> explicit backward tape -> gradients gathered into one flat buffer }
+    [NCCL all-reduce of the flat gradient buffer when world_size > 1]
+    one fused Adam launch over the flat parameter buffer
+
+The teacher is forward-only (its gradients never influence the student update; the reference's teacher
+backward is wasted work). `plain=True` drops the teacher (function.train semantics,
+function.py:44-63).
+"""
+import torch
+
+from . import ops
+from . import _native as N
+
+
+class FlatParams:
+    """Re-homes a module's parameters as views into one flat fp32 buffer (needed for the single all-reduce and the
+    single Adam launch). Parameter objects are preserved (only .data changes), so optimizers / state_dict keep
+    working."""
+
+    def __init__(self, net):
+        self.params = [p for p in net.parameters()]
+        dev = self.params[0].device
+        sizes = [p.numel() for p in self.params]
+        # pad every tensor to a multiple of 4 floats so float4 kernels can run over the flat buffer
+        self.offsets = []
+        off = 0
+        for n in sizes:
+            self.offsets.append(off)
+            off += (n + 3) // 4 * 4
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad_views = []
+        for p, o in zip(self.params, self.offsets):
+            v = self.flat[o:o + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+            self.grad_views.append(self.grad[o:o + p.numel()].view(p.shape))
+
+    def is_intact(self):
+        base = self.flat.untyped_storage().data_ptr()
+        return all(p.data.untyped_storage().data_ptr() == base for p in self.params)
+
+
+class FPDTrainStep:
+    def __init__(self, student, teacher=None, alpha=0.5, lr=2.5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 process_group=None, use_graph=True):
+        self.student, self.teacher = student, teacher
+        self.alpha = float(alpha) if teacher is not None else 0.0
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.flat = FlatParams(student)
+        self.exp_avg = torch.zeros_like(self.flat.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat.flat)
+        self.step_count = 0
+        self.use_graph = use_graph
+        self.graph = None
+        self.static = None
+        self.losses = None
+        self.launches_per_step = None
+        student.train()
+        if teacher is not None:
+            teacher.eval()
+
+    # ------------------------------------------------------------------ the graph body
+    def _body(self, x, target, tw):
+        s_eng = self.student.engine()
+        ctx = s_eng.forward(x, True, record_tape=True)
+        outs = [v.data for v in ctx.outs]
+        t_last = None
+        if self.teacher is not None:
+            t_ctx = self.teacher.engine().forward(x, False, record_tape=False)
+            t_last = t_ctx.outs[-1].data
+        losses, grads = ops.fpd_loss(outs, target, t_last, tw, self.alpha, losses_out=self.losses)
+        pg = s_eng.backward(ctx, grads)
+        srcs, dsts = [], []
+        for p, gv in zip(self.flat.params, self.flat.grad_views):
+            g = pg.get(p)
+            if g is None:
+                gv.zero_()
+            else:
+                srcs.append(g.reshape(p.shape))
+                dsts.append(gv)
+        torch._foreach_copy_(dsts, srcs)
+        return losses
+
+    def _capture(self, x, target, tw):
+        self.static = (torch.empty_like(x), torch.empty_like(target), torch.empty_like(tw))
+        for s, v in zip(self.static, (x, target, tw)):
+            s.copy_(v)
+        self.losses = torch.zeros(3, dtype=torch.float32, device=x.device)
+        # eager warm-up (lazy init, workspace growth, running-stat semantics identical to a normal step)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._saved_bn = self._snapshot_bn()
+            self._body(*self.static)
+            self._restore_bn(self._saved_bn)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = N.lib().fpd_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body(*self.static)
+        self.launches_per_step = int(N.lib().fpd_launch_count() - n0) + 1  # + the Adam launch
+        self._restore_bn(self._saved_bn)  # capture does not execute, but keep host-side state tidy
+
+    def _snapshot_bn(self):
+        return [b.clone() for b in self.student.buffers()]
+
+    def _restore_bn(self, saved):
+        for b, s in zip(self.student.buffers(), saved):
+            b.copy_(s)
+
+    # ------------------------------------------------------------------ public
+    def step(self, x, target, target_weight):
+        """x [B,3,H,W], target [B,J,h,w], target_weight [B,J,1] -- CUDA or pinned-host tensors.
+        Returns the device tensor losses[3] = (pose, kd, total); no host synchronisation."""
+        tw = target_weight.reshape(target_weight.shape[0], -1)
+        if self.use_graph:
+            if self.graph is None:
+                xd, td, wd = (t.cuda(non_blocking=True).float().contiguous() for t in (x, target, tw))
+                self._capture(xd, td, wd)
+            for s, v in zip(self.static, (x, target, tw)):
+                s.copy_(v, non_blocking=True)
+            self.graph.replay()
+            losses = self.losses
+        else:
+            xd, td, wd = (t.cuda(non_blocking=True).float().contiguous() for t in (x, target, tw))
+            if self.losses is None:
+                self.losses = torch.zeros(3, dtype=torch.float32, device=xd.device)
+            n0 = N.lib().fpd_launch_count()
+            losses = self._body(xd, td, wd)
+            self.launches_per_step = int(N.lib().fpd_launch_count() - n0) + 1
+        gscale = 1.0
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat.grad, group=self.pg)
+            gscale = 1.0 / self.world
+        self.step_count += 1
+        ops.adam_flat(self.flat.flat, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0],
+                      self.betas[1], self.eps, self.wd, self.step_count, grad_scale=gscale)
+        return losses

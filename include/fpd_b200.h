@@ -38,6 +38,8 @@ typedef struct CUstream_st* fpd_stream_t;
 const char* fpd_last_error(void);
 int fpd_version(void);
 int fpd_sm_count(void);
+/* number of kernels this library has launched in this process (monotonic) */
+long long fpd_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------------
  * Convolution. Replaces nn.Conv2d -> cuDNN/oneDNN as used by lib/models/hourglass.py:20-27 (Bottleneck

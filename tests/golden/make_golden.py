@@ -65,7 +65,7 @@ def main():
     exec(compile(src, "ref_nms.py", "exec"), nms_ns)
 
     rng = np.random.RandomState(0)
-    B, H, W, J = 2, 64, 64, 16
+    B, H, W, J = 2, 128, 128, 16  # 32x32 heat-maps: deepest hourglass level is 2x2 (well-conditioned BN)
     h, w = H // 4, W // 4
 
     # ---- 1. hourglass s=2 f=64, train mode, plain MSE (function.train semantics, function.py:44-63) ----

@@ -93,6 +93,41 @@ def test_conv2d_tc_dgrad_with_relu_mask(shape):
     assert relerr(nchw(dx), dx_ref) < 2e-5
 
 
+WGRAD_TC_SHAPES = [
+    # B, H, W, Cin, Cout, k
+    (2, 64, 64, 64, 64, 3),     # student conv2 (tap pairs stacked on M)
+    (2, 64, 64, 128, 64, 1),    # student conv1
+    (2, 64, 64, 64, 128, 1),    # student conv3 (dY side on M)
+    (2, 64, 64, 128, 128, 1),   # fc / fc_
+    (4, 16, 16, 64, 64, 3),
+    (8, 4, 4, 64, 64, 3),
+    (3, 8, 8, 128, 64, 1),      # ragged batch tile
+    (2, 128, 128, 32, 32, 3),   # layer1 conv2 (4 taps stacked)
+    (1, 32, 32, 128, 128, 3),
+    (2, 64, 48, 32, 32, 3),
+    (2, 32, 32, 128, 256, 1),
+]
+
+
+@pytest.mark.parametrize("shape", WGRAD_TC_SHAPES)
+@pytest.mark.parametrize("passes", [3, 1])
+def test_conv2d_wgrad_tc(shape, passes):
+    B, H, W, Cin, Cout, k = shape
+    o = ops()
+    assert o.conv2d_wgrad_tc_supported(Cin, Cout, k)
+    g = torch.Generator(device="cuda").manual_seed(77)
+    a = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.zeros(Cout, Cin, k, k, device="cuda", requires_grad=True)
+    dy = torch.randn(B, Cout, H, W, device="cuda", generator=g)
+    (dw_ref,) = torch.autograd.grad(F.conv2d(a, w, None, padding=k // 2), w, dy)
+    a_hi, a_lo = o.affine_act_split(nhwc(a), split=(passes == 3))
+    g_hi, g_lo = o.affine_act_split(nhwc(dy), split=(passes == 3))
+    dw = o.conv2d_wgrad_tc(a_hi, a_lo, g_hi, g_lo, k)
+    torch.cuda.synchronize()
+    err = relerr(dw, dw_ref)
+    assert err < (2e-5 if passes == 3 else 3e-3), "wgrad_tc %s passes=%d rel err %.3e" % (shape, passes, err)
+
+
 @pytest.mark.parametrize("cfg", [
     # B, H, W, Cin, Cout, k, stride, pad
     (2, 64, 64, 3, 32, 7, 2, 3),
