@@ -127,7 +127,7 @@ def cpu_fpd_steps(B, max_steps, max_seconds, warmup=1, as_written=False):
     from oracle import hourglass_oracle as O
     import fpd_b200  # noqa: F401
     from fpd_b200.lib.models import hourglass as H  # parameter containers only (no compute on CPU)
-    threads = os.cpu_count() or 1
+    threads = int(os.environ.get("FPD_CPU_THREADS", "0")) or len(os.sched_getaffinity(0))
     torch.set_num_threads(threads)
     torch.manual_seed(0)
     s_sd = {k: v.clone() for k, v in H.get_pose_net(cfg(128, 4), True).state_dict().items()}

@@ -216,14 +216,24 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //  bits [0,14)  start address >> 4      bits [16,30) leading byte offset >> 4
 //  bits [32,46) stride byte offset >> 4 bits [46,48) version (1 on sm_100)
 //  bits [49,52) base offset             bits [61,64) layout (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(layout_type & 7) << 61;
   return d;
+}
+// K-major operand tile, 128-byte rows, SWIZZLE_128B (TMA: CU_TENSOR_MAP_SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return umma_desc(smem_addr, lbo_bytes, sbo_bytes, 2);
+}
+// MN-major tf32 operand tile: the only legal swizzle is "128B with 32-byte atoms" (layout type 1, Swizzle<2,5,2>:
+// 32-byte chunk index ^= row & 3, 4-row / 512-byte pattern; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+__device__ __forceinline__ uint64_t umma_desc_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return umma_desc(smem_addr, lbo_bytes, sbo_bytes, 1);
 }
 // Instruction descriptor for kind::tf32 with fp32 accumulation.
 //  [4,6) c_format=1(F32)  [7,10) a_format=2(TF32)  [10,13) b_format=2  [15] a_major  [16] b_major

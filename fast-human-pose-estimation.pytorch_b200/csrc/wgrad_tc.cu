@@ -9,6 +9,8 @@
 // GEMM view: the contraction runs over PIXELS, so both operands are read "transposed": a TMA box of
 // [32 pixels x 32 channels] (128-byte rows, SWIZZLE_128B) is exactly the canonical *MN-major* UMMA operand
 // tile (channels contiguous = the M/N axis, pixels = K, 8-pixel swizzle atoms). No transposition pass and no
+// (tf32 MN-major operands must use the "128B swizzle with 32-byte atoms" layout: TMA SWIZZLE_128B_ATOM_32B <->
+// UMMA layout type SWIZZLE_128B_BASE32B, 4-row atoms, SBO = 512 B.)
 // im2col: a 3x3 tap is a shifted TMA box with hardware zero fill, and taps are *stacked along M*:
 //   mode A (activation side on M): M = 128 = G taps x Cin (Cin in {32,64,128}, G = 128/Cin), N = Cout
 //   mode B (dY side on M, 1x1 only): M = 128 output channels, N = Cin
@@ -126,13 +128,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const uint32_t n_lo = m_lo + 4 * kBoxBytes;
 #pragma unroll
         for (int ks = 0; ks < kKp / 8; ++ks) {
-          const uint32_t koff = ks * 1024;  // 8 pixels = one 8-row swizzle atom
-          const uint64_t dm_hi = umma_desc_sw128(m_hi + koff, kBoxBytes, 1024);
-          const uint64_t dn_hi = umma_desc_sw128(n_hi + koff, kBoxBytes, 1024);
+          const uint32_t koff = ks * 1024;  // 8 pixels = two 4-row (512 B) swizzle atoms; SBO = 512 steps between them
+          const uint64_t dm_hi = umma_desc_sw128_32b(m_hi + koff, kBoxBytes, 512);
+          const uint64_t dn_hi = umma_desc_sw128_32b(n_hi + koff, kBoxBytes, 512);
           uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
           if (p.passes == 3) {
-            const uint64_t dm_lo = umma_desc_sw128(m_lo + koff, kBoxBytes, 1024);
-            const uint64_t dn_lo = umma_desc_sw128(n_lo + koff, kBoxBytes, 1024);
+            const uint64_t dm_lo = umma_desc_sw128_32b(m_lo + koff, kBoxBytes, 512);
+            const uint64_t dn_lo = umma_desc_sw128_32b(n_lo + koff, kBoxBytes, 512);
             umma_tf32(tmem_base, dm_lo, dn_hi, idesc, acc);
             umma_tf32(tmem_base, dm_hi, dn_lo, idesc, 1u);
             acc = 1u;
@@ -283,17 +285,17 @@ int wgrad_tc_launch(const float* a_hi, const float* a_lo, const float* dy_hi, co
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
-    int rc = encode_tmap(&tm_a_hi, a_hi, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = encode_tmap(&tm_a_hi, a_hi, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    rc = encode_tmap(&tm_a_lo, a_lo ? a_lo : a_hi, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = encode_tmap(&tm_a_lo, a_lo ? a_lo : a_hi, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
   {
     uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)Cout * 4, (uint64_t)W * Cout * 4, (uint64_t)H * W * Cout * 4};
-    int rc = encode_tmap(&tm_g_hi, dy_hi, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = encode_tmap(&tm_g_hi, dy_hi, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    rc = encode_tmap(&tm_g_lo, dy_lo ? dy_lo : dy_hi, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = encode_tmap(&tm_g_lo, dy_lo ? dy_lo : dy_hi, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
   static bool attr_set = false;

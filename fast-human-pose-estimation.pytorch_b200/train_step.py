@@ -144,8 +144,8 @@ class FPDTrainStep:
             self.launches_per_step = int(N.lib().fpd_launch_count() - n0) + 1
         gscale = 1.0
         if self.world > 1:
-            torch.distributed.all_reduce(self.flat.grad, group=self.pg)
-            gscale = 1.0 / self.world
+            from .parallel import allreduce_mean_
+            gscale = allreduce_mean_(self.flat.grad, self.pg)
         self.step_count += 1
         ops.adam_flat(self.flat.flat, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0],
                       self.betas[1], self.eps, self.wd, self.step_count, grad_scale=gscale)
