@@ -127,7 +127,9 @@ def cpu_fpd_steps(B, max_steps, max_seconds, warmup=1, as_written=False):
     from oracle import hourglass_oracle as O
     import fpd_b200  # noqa: F401
     from fpd_b200.lib.models import hourglass as H  # parameter containers only (no compute on CPU)
-    threads = int(os.environ.get("FPD_CPU_THREADS", "0")) or len(os.sched_getaffinity(0))
+    # measured on the 128-thread B200 host (gpurun_out/cpu_threads.log): 16 threads 5.2 img/s, 32: 3.3, 64: 1.4,
+    # 128: 0.09 -- the batch-4 sample cannot use more threads productively, so cap at 16 unless overridden
+    threads = int(os.environ.get("FPD_CPU_THREADS", "0")) or min(16, len(os.sched_getaffinity(0)))
     torch.set_num_threads(threads)
     torch.manual_seed(0)
     s_sd = {k: v.clone() for k, v in H.get_pose_net(cfg(128, 4), True).state_dict().items()}

@@ -30,7 +30,9 @@ _SIGNATURES = {
     "fpd_conv2d_wgrad_tc": (c_int, [P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),
     "fpd_conv2d_simt_fwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "fpd_conv2d_simt_dgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
-    "fpd_conv2d_simt_wgrad": (c_int, [P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "fpd_conv2d_simt_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "fpd_conv2d_simt_wgrad": (c_int, [P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P,
+                                      c_size_t, P]),
     "fpd_weight_prep": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     "fpd_bn_stats_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "fpd_bn_stats": (c_int, [P, c_int64, c_int, P, P, P, c_size_t, P]),

@@ -112,9 +112,13 @@ int fpd_conv2d_simt_dgrad(const float* dy, const float* w, float* dx, int B, int
                           int stride, int pad, fpd_stream_t stream) {
   return conv_simt_dgrad(dy, w, dx, B, H, W, Cin, Cout, k, stride, pad, S(stream));
 }
+size_t fpd_conv2d_simt_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout, int k, int stride, int pad) {
+  return conv_simt_wgrad_workspace_bytes(B, H, W, Cin, Cout, k, stride, pad);
+}
 int fpd_conv2d_simt_wgrad(const float* x, const float* dy, float* dw, float scale, int B, int H, int W, int Cin,
-                          int Cout, int k, int stride, int pad, fpd_stream_t stream) {
-  return conv_simt_wgrad(x, dy, dw, scale, B, H, W, Cin, Cout, k, stride, pad, S(stream));
+                          int Cout, int k, int stride, int pad, void* workspace, size_t workspace_bytes,
+                          fpd_stream_t stream) {
+  return conv_simt_wgrad(x, dy, dw, scale, B, H, W, Cin, Cout, k, stride, pad, workspace, workspace_bytes, S(stream));
 }
 int fpd_weight_prep(const float* w, float* w_hi, float* w_lo, int O, int I, int k, int for_dgrad,
                     fpd_stream_t stream) {

@@ -102,12 +102,15 @@ bn_stats_partial_kernel(const float* __restrict__ x, int64_t P, int C, int L, in
   }
 }
 
+// one warp per channel: each lane Chan-merges a strided subset of the block partials, then the lanes merge by
+// shuffle (fixed order -> deterministic).
 __global__ void bn_stats_final_kernel(const double* __restrict__ part, int nblocks, int64_t rows_per_block,
                                       int64_t P, int C, float* __restrict__ mean, float* __restrict__ var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double na = 0.0, ma = 0.0, m2a = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
+  for (int b = lane; b < nblocks; b += 32) {
     int64_t r0 = (int64_t)b * rows_per_block, r1 = r0 + rows_per_block;
     if (r1 > P) r1 = P;
     const double nb = (double)(r1 - r0);
@@ -120,8 +123,25 @@ __global__ void bn_stats_final_kernel(const double* __restrict__ part, int nbloc
     m2a += m2b + delta * delta * (na * nb / nt);
     na = nt;
   }
-  mean[c] = (float)ma;
-  var[c] = (float)(m2a / (double)P);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double nb = __shfl_xor_sync(0xffffffffu, na, o);
+    const double mb = __shfl_xor_sync(0xffffffffu, ma, o);
+    const double m2b = __shfl_xor_sync(0xffffffffu, m2a, o);
+    const double nt = na + nb;
+    if (nt > 0.0) {
+      // symmetric form so both partners compute the identical merged triple
+      const double mean_t = (na * ma + nb * mb) / nt;
+      const double delta = mb - ma;
+      m2a = m2a + m2b + delta * delta * (na * nb / nt);
+      ma = mean_t;
+      na = nt;
+    }
+  }
+  if (lane == 0) {
+    mean[c] = (float)ma;
+    var[c] = (float)(m2a / (double)P);
+  }
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ mean, const float* __restrict__ var,
@@ -202,13 +222,16 @@ channel_reduce_partial_kernel(F f, int64_t P, int C, int L, int R, int64_t rows_
   }
 }
 
+// one warp per output value; lanes sum a strided subset of the block partials, then a fixed-order shuffle tree
 __global__ void channel_reduce_final_kernel(const double* __restrict__ part, int nblocks, int n /*NV*C*/,
                                             float scale, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= n) return;
   double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += part[(size_t)b * n + i];
-  out[i] = (float)(s * (double)scale);
+  for (int b = lane; b < nblocks; b += 32) s += part[(size_t)b * n + i];
+  s = warp_sum(s);
+  if (lane == 0) out[i] = (float)(s * (double)scale);
 }
 
 struct SumFunctor {
@@ -516,7 +539,7 @@ int bn_stats(const float* x, int64_t P, int C, float* mean, float* var_biased, v
   bn_stats_partial_kernel<<<g.nblocks, kRedThreads, smem, stream>>>(x, P, C, g.L, g.R, g.rows_per_block,
                                                                     (double*)workspace);
   FPD_LAUNCH_CHECK();
-  bn_stats_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>((const double*)workspace, g.nblocks,
+  bn_stats_final_kernel<<<(C * 32 + 127) / 128, 128, 0, stream>>>((const double*)workspace, g.nblocks,
                                                              g.rows_per_block, P, C, mean, var_biased);
   FPD_LAUNCH_CHECK();
   return FPD_OK;
@@ -634,7 +657,7 @@ static int run_channel_reduce(F f, int64_t P, int C, float scale, float* out, vo
                                                                                   g.rows_per_block,
                                                                                   (double*)workspace);
   FPD_LAUNCH_CHECK();
-  channel_reduce_final_kernel<<<(NV * C + 127) / 128, 128, 0, stream>>>((const double*)workspace, g.nblocks, NV * C,
+  channel_reduce_final_kernel<<<(NV * C * 32 + 127) / 128, 128, 0, stream>>>((const double*)workspace, g.nblocks, NV * C,
                                                                         scale, out);
   FPD_LAUNCH_CHECK();
   return FPD_OK;

@@ -27,8 +27,9 @@ int conv_simt_fwd(const float* x, const float* w_oihw, const float* bias, const 
                   int H, int W, int Cin, int Cout, int k, int stride, int pad, cudaStream_t stream);
 int conv_simt_dgrad(const float* dy, const float* w_oihw, float* dx, int B, int H, int W, int Cin, int Cout, int k,
                     int stride, int pad, cudaStream_t stream);  // H,W = input size; dx[B,H,W,Cin]
+size_t conv_simt_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout, int k, int stride, int pad);
 int conv_simt_wgrad(const float* x, const float* dy, float* dw_oihw, float scale, int B, int H, int W, int Cin,
-                    int Cout, int k, int stride, int pad, cudaStream_t stream);
+                    int Cout, int k, int stride, int pad, void* workspace, size_t ws_bytes, cudaStream_t stream);
 
 // ---- elementwise.cu ----
 // Per-channel batch statistics of x[P,C] (numerically robust: per-chunk shifted sums, Chan merge in fp64).

@@ -112,8 +112,9 @@ def conv2d_simt_wgrad(x, dy, k, stride=1, pad=0, scale=1.0, out=None):
     B, H, W, Cin = x.shape
     Cout = dy.shape[-1]
     dw = out if out is not None else torch.empty((Cout, Cin, k, k), dtype=torch.float32, device=x.device)
+    ws = _ws.get(N.lib().fpd_conv2d_simt_wgrad_workspace_bytes(B, H, W, Cin, Cout, k, stride, pad), x.device)
     N.check(N.lib().fpd_conv2d_simt_wgrad(_p(x), _p(dy), _p(dw), float(scale), B, H, W, Cin, Cout, k, stride, pad,
-                                          _stream()), "conv2d_simt_wgrad")
+                                          _p(ws), ws.numel(), _stream()), "conv2d_simt_wgrad")
     return dw
 
 

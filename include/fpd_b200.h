@@ -73,8 +73,10 @@ int fpd_conv2d_simt_fwd(const float* x, const float* w_oihw, const float* bias, 
                         int B, int H, int W, int Cin, int Cout, int k, int stride, int pad, fpd_stream_t stream);
 int fpd_conv2d_simt_dgrad(const float* dy, const float* w_oihw, float* dx, int B, int H, int W, int Cin, int Cout,
                           int k, int stride, int pad, fpd_stream_t stream);
+size_t fpd_conv2d_simt_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout, int k, int stride, int pad);
 int fpd_conv2d_simt_wgrad(const float* x, const float* dy, float* dw_oihw, float scale, int B, int H, int W,
-                          int Cin, int Cout, int k, int stride, int pad, fpd_stream_t stream);
+                          int Cin, int Cout, int k, int stride, int pad, void* workspace, size_t workspace_bytes,
+                          fpd_stream_t stream);
 
 /* OIHW fp32 -> tensor-core operand layout, split into tf32 hi/lo (w_lo may be NULL).
  * for_dgrad=0: [tap][O][I]; for_dgrad=1: [taps-1-tap][I][O] (180-degree flipped, transposed). */
