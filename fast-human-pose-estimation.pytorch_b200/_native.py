@@ -39,6 +39,9 @@ _SIGNATURES = {
     "fpd_bn_finalize": (c_int, [P, P, P, P, c_float, c_int64, P, P, P, P, P, c_float, c_int, P]),
     "fpd_affine_act_split": (c_int, [P, P, P, P, c_int, P, P, c_int64, c_int, P]),
     "fpd_affine_act": (c_int, [P, P, P, P, c_int, P, c_int64, c_int, P]),
+    "fpd_affine_add_act": (c_int, [P, P, P, P, P, c_int, P, c_int64, c_int, P]),
+    "fpd_fuse_sum": (c_int, [POINTER(c_void_p), POINTER(c_int), c_int, c_int, P, c_int, c_int, c_int, c_int, P]),
+    "fpd_upsample_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "fpd_channel_reduce_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "fpd_channel_sum": (c_int, [P, c_int64, c_int, c_float, P, P, c_size_t, P]),
     "fpd_bn_bwd_reduce": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int, P, P, c_size_t, P]),

@@ -143,6 +143,18 @@ int fpd_affine_act(const float* x, const float* mean, const float* scale, const 
                    int64_t P, int C, fpd_stream_t stream) {
   return affine_act(x, mean, scale, shift, relu, y, P, C, S(stream));
 }
+int fpd_affine_add_act(const float* x, const float* mean, const float* scale, const float* shift,
+                       const float* residual, int relu, float* y, int64_t P, int C, fpd_stream_t stream) {
+  return affine_add_act(x, mean, scale, shift, residual, relu, y, P, C, S(stream));
+}
+int fpd_fuse_sum(const float* const* terms_host, const int* shifts_host, int n, int relu, float* out, int B, int H,
+                 int W, int C, fpd_stream_t stream) {
+  FPD_REQUIRE(terms_host && shifts_host, "fpd_fuse_sum: NULL term table");
+  return fuse_sum(terms_host, shifts_host, n, relu, out, B, H, W, C, S(stream));
+}
+int fpd_upsample_bwd(const float* dout, float* dlow, int shift, int B, int H, int W, int C, fpd_stream_t stream) {
+  return upsample_bwd(dout, dlow, shift, B, H, W, C, S(stream));
+}
 size_t fpd_channel_reduce_workspace_bytes(int64_t P, int C) { return channel_reduce_workspace_bytes(P, C); }
 int fpd_channel_sum(const float* dy, int64_t P, int C, float scale, float* out, void* ws, size_t wsb,
                     fpd_stream_t stream) {

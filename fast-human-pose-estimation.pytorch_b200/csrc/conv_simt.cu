@@ -217,20 +217,23 @@ conv_wgrad_partial_kernel(const float* __restrict__ x, const float* __restrict__
   }
 }
 
+// one warp per weight element; lanes sum a strided subset of the chunk partials, then a fixed-order shuffle tree
 __global__ void conv_wgrad_final_kernel(const float* __restrict__ partial, float* __restrict__ dw, float scale,
                                         int nchunks, int Cin, int Cout, int taps) {
   const int CoutP8 = (Cout + 7) & ~7;
   const int K = taps * Cin;
   const int64_t total = (int64_t)Cout * Cin * taps;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int tap = (int)(i % taps);
-    const int ci = (int)((i / taps) % Cin);
-    const int co = (int)(i / ((int64_t)taps * Cin));
-    const size_t off = (size_t)(tap * Cin + ci) * CoutP8 + co;
-    double s = 0.0;
-    for (int c = 0; c < nchunks; ++c) s += (double)partial[(size_t)c * K * CoutP8 + off];
-    dw[i] = (float)(s * (double)scale);
-  }
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= total) return;
+  const int tap = (int)(i % taps);
+  const int ci = (int)((i / taps) % Cin);
+  const int co = (int)(i / ((int64_t)taps * Cin));
+  const size_t off = (size_t)(tap * Cin + ci) * CoutP8 + co;
+  double s = 0.0;
+  for (int c = lane; c < nchunks; c += 32) s += (double)partial[(size_t)c * K * CoutP8 + off];
+  s = warp_sum(s);
+  if (lane == 0) dw[i] = (float)(s * (double)scale);
 }
 
 inline int grid_for(int64_t n, int threads) {
@@ -324,8 +327,8 @@ int conv_simt_wgrad(const float* x, const float* dy, float* dw_oihw, float scale
                                                               pad, Ho, Wo, g.chunk);
   FPD_LAUNCH_CHECK();
   const int64_t total = (int64_t)Cout * Cin * k * k;
-  conv_wgrad_final_kernel<<<grid_for(total, 128), 128, 0, stream>>>((const float*)workspace, dw_oihw, scale, g.nchunks,
-                                                                    Cin, Cout, k * k);
+  conv_wgrad_final_kernel<<<(unsigned)((total * 32 + 127) / 128), 128, 0, stream>>>((const float*)workspace, dw_oihw,
+                                                                                    scale, g.nchunks, Cin, Cout, k * k);
   FPD_LAUNCH_CHECK();
   return FPD_OK;
 }

@@ -91,7 +91,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int kblocks_per_tap = p.Cin / kBlockK;
+  const int kblocks_per_tap = (p.Cin + kBlockK - 1) / kBlockK;  // a ragged last block is zero-filled by TMA
   const int kblocks = p.taps * kblocks_per_tap;
 
   if (warp == 0) {
@@ -240,7 +240,9 @@ int pow2_floor_div(int x, int cap) {  // largest power of two dividing x, capped
 }  // namespace
 
 bool conv_tc_supported(int Cin, int Cout, int ksize) {
-  return (ksize == 1 || ksize == 3) && Cin % 32 == 0 && Cin >= 32 && Cout % 16 == 0 && Cout >= 16 && Cout <= 256;
+  // Cin need not be a multiple of the 32-channel k-block: the TMA unit zero-fills the out-of-bounds channels of
+  // both operands (16-channel score_ convs, HRNet-w48's 48/96-channel branches)
+  return (ksize == 1 || ksize == 3) && Cin % 4 == 0 && Cin >= 4 && Cout % 16 == 0 && Cout >= 16 && Cout <= 256;
 }
 
 int conv_tc_launch(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, const float* bias,

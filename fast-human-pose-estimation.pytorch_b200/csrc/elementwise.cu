@@ -271,7 +271,8 @@ struct BnBwdFunctor {
 __global__ void affine_act_split_kernel(const float4* __restrict__ x, const float* __restrict__ mean,
                                         const float* __restrict__ scale,
                                         const float* __restrict__ shift, int relu, float4* __restrict__ hi,
-                                        float4* __restrict__ lo, int64_t n4, int L, int round) {
+                                        float4* __restrict__ lo, int64_t n4, int L, int round,
+                                        const float4* __restrict__ residual = nullptr) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = __ldg(x + i);
     if (scale) {
@@ -281,6 +282,10 @@ __global__ void affine_act_split_kernel(const float4* __restrict__ x, const floa
       const float4 mu = mean ? __ldg(reinterpret_cast<const float4*>(mean) + cx) : make_float4(0.f, 0.f, 0.f, 0.f);
       v.x = fmaf(v.x - mu.x, sc.x, sh.x); v.y = fmaf(v.y - mu.y, sc.y, sh.y);
       v.z = fmaf(v.z - mu.z, sc.z, sh.z); v.w = fmaf(v.w - mu.w, sc.w, sh.w);
+    }
+    if (residual) {
+      const float4 r = __ldg(residual + i);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
     }
     if (relu) {
       v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
@@ -507,6 +512,59 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, float* __restric
   }
 }
 
+
+// ---- HRNet glue (reference lib/models/pose_hrnet.py:256-263 fuse, :41-57 BasicBlock tail) -------------------
+struct FuseTerms {
+  const float4* t[4];
+  int shift[4];  // log2 of the nearest-neighbour upsampling factor of each term
+  int n;
+};
+
+// out[b,h,w,:] = relu?( sum_j t_j[b, h >> s_j, w >> s_j, :] ), summed in term order like the reference's
+// `y = y + fuse_layers[i][j](x[j])` loop
+__global__ void fuse_sum_kernel(FuseTerms ft, int relu, float4* __restrict__ out, int B, int H, int W, int L) {
+  const int64_t n = (int64_t)B * H * W * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % L);
+    int64_t t = i / L;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int b = (int)(t / H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < ft.n; ++j) {
+      const int s = ft.shift[j];
+      const int hs = H >> s, wsz = W >> s;
+      const float4 v = __ldg(ft.t[j] + (((int64_t)b * hs + (h >> s)) * wsz + (w >> s)) * L + cx);
+      if (j == 0) acc = v;
+      else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    }
+    if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+    out[i] = acc;
+  }
+}
+
+// dlow[b,ho,wo,:] = sum over the f x f block of dout (f = 1 << shift); Ho,Wo = low-res size
+__global__ void upsample_bwd_kernel(const float4* __restrict__ dout, float4* __restrict__ dlow, int shift, int B,
+                                    int Ho, int Wo, int L) {
+  const int64_t n = (int64_t)B * Ho * Wo * L;
+  const int f = 1 << shift;
+  const int W = Wo << shift, H = Ho << shift;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % L);
+    int64_t t = i / L;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int dy = 0; dy < f; ++dy)
+      for (int dx = 0; dx < f; ++dx) {
+        const float4 v = __ldg(dout + (((int64_t)b * H + (ho * f + dy)) * W + (wo * f + dx)) * L + cx);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    dlow[i] = acc;
+  }
+}
+
 inline int grid_for(int64_t n, int threads) {
   int64_t b = (n + threads - 1) / threads;
   const int64_t cap = 148 * 16;
@@ -702,6 +760,46 @@ int weight_prep(const float* w_oihw, float* w_hi, float* w_lo, int O, int I, int
                 cudaStream_t stream) {
   const int64_t n = (int64_t)O * I * k * k;
   weight_prep_kernel<<<grid_for(n, 256), 256, 0, stream>>>(w_oihw, w_hi, w_lo, O, I, k, for_dgrad);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int affine_add_act(const float* x, const float* mean, const float* scale, const float* shift, const float* residual,
+                   int relu, float* y, int64_t P, int C, cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0, "affine_add_act: C=%d must be a multiple of 4", C);
+  FPD_REQUIRE((scale == nullptr) == (shift == nullptr), "affine_add_act: scale/shift must come in pairs");
+  const int64_t n4 = P * C / 4;
+  affine_act_split_kernel<<<grid_for(n4, 256), 256, 0, stream>>>((const float4*)x, mean, scale, shift, relu,
+                                                                 (float4*)y, nullptr, n4, C / 4, 0,
+                                                                 (const float4*)residual);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int fuse_sum(const float* const* terms, const int* shifts, int n, int relu, float* out, int B, int H, int W, int C,
+             cudaStream_t stream) {
+  FPD_REQUIRE(n >= 1 && n <= 4, "fuse_sum: 1..4 terms, got %d", n);
+  FPD_REQUIRE(C % 4 == 0, "fuse_sum: C=%d must be a multiple of 4", C);
+  FuseTerms ft{};
+  ft.n = n;
+  for (int j = 0; j < n; ++j) {
+    FPD_REQUIRE(shifts[j] >= 0 && (H % (1 << shifts[j])) == 0 && (W % (1 << shifts[j])) == 0,
+                "fuse_sum: term %d upsampling factor does not divide the output size", j);
+    ft.t[j] = (const float4*)terms[j];
+    ft.shift[j] = shifts[j];
+  }
+  const int64_t n4 = (int64_t)B * H * W * (C / 4);
+  fuse_sum_kernel<<<grid_for(n4, 256), 256, 0, stream>>>(ft, relu, (float4*)out, B, H, W, C / 4);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int upsample_bwd(const float* dout, float* dlow, int shift, int B, int H, int W, int C, cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0 && shift >= 0 && H % (1 << shift) == 0 && W % (1 << shift) == 0,
+              "upsample_bwd: bad shape H=%d W=%d C=%d shift=%d", H, W, C, shift);
+  const int Ho = H >> shift, Wo = W >> shift;
+  const int64_t n = (int64_t)B * Ho * Wo * (C / 4);
+  upsample_bwd_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const float4*)dout, (float4*)dlow, shift, B, Ho, Wo, C / 4);
   FPD_LAUNCH_CHECK();
   return FPD_OK;
 }

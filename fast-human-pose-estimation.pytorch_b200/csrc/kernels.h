@@ -46,6 +46,14 @@ int affine_act_split(const float* x, const float* mean, const float* scale, cons
 // y = act(x*scale+shift), full fp32 (no operand rounding)
 int affine_act(const float* x, const float* mean, const float* scale, const float* shift, int relu, float* y,
                int64_t P, int C, cudaStream_t stream);
+// y = act((x-mean)*scale+shift + residual): tail of the post-activation residual blocks (pose_hrnet.py:48-55)
+int affine_add_act(const float* x, const float* mean, const float* scale, const float* shift, const float* residual,
+                   int relu, float* y, int64_t P, int C, cudaStream_t stream);
+// out = relu?(sum_j nearest_up_{2^shift_j}(term_j)) (HRNet fuse, pose_hrnet.py:256-263); terms/shifts: host arrays
+int fuse_sum(const float* const* terms, const int* shifts, int n, int relu, float* out, int B, int H, int W, int C,
+             cudaStream_t stream);
+// dlow = sum over (2^shift)^2 blocks of dout [B,H,W,C]
+int upsample_bwd(const float* dout, float* dlow, int shift, int B, int H, int W, int C, cudaStream_t stream);
 int maxpool2x2_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream);
 int maxpool2x2_bwd(const float* x, const float* dy, float* dx, int accumulate, int B, int H, int W, int C,
                    cudaStream_t stream);

@@ -223,8 +223,10 @@ Plan make_plan(int Cin, int Cout, int ksize) {
     pl.ok = true; pl.mode_b = 0; pl.G = 128 / Cin; pl.groups = (taps + pl.G - 1) / pl.G; pl.N = Cout;
     return pl;
   }
-  if (ksize == 1 && Cout % 128 == 0 && Cin % 32 == 0 && Cin >= 32 && Cin <= 256) {
-    pl.ok = true; pl.mode_b = 1; pl.G = 1; pl.groups = Cout / 128; pl.N = Cin;
+  // mode B: dY channels on M in tiles of 128; channel counts that are not multiples of 128 / 32 are completed by the
+  // TMA unit's out-of-bounds zero fill (costs no memory traffic), e.g. the 16-channel score convs or 32->64 1x1s.
+  if (ksize == 1 && Cout % 4 == 0 && Cin % 4 == 0 && Cin >= 4 && Cin <= 256) {
+    pl.ok = true; pl.mode_b = 1; pl.G = 1; pl.groups = (Cout + 127) / 128; pl.N = (Cin + 31) / 32 * 32;
     return pl;
   }
   return pl;

@@ -324,6 +324,10 @@ class Engine:
                 x = self.conv(ctx, score, "score_.%d" % i, residual=t)
         return outs
 
+    def run_network(self, ctx, img_nchw):
+        """Topology hook: subclasses (engine_hrnet.HRNetEngine) override this."""
+        return self.hourglass_net(ctx, img_nchw)
+
     # ------------------------------------------------------------------ entry points
     def forward(self, img_nchw, training, record_tape):
         ctx = _Ctx()
@@ -338,7 +342,7 @@ class Engine:
             if record_tape:
                 w = PreparedWeights(self.convs.values(), ctx.passes, need_dgrad=True)
             ctx.weights, ctx.affine = w, affine
-        outs = self.hourglass_net(ctx, img_nchw.contiguous().float())
+        outs = self.run_network(ctx, img_nchw.contiguous().float())
         if ctx.nbt:
             torch._foreach_add_(ctx.nbt, 1)
         ctx.outs = outs

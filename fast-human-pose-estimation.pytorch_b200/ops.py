@@ -78,6 +78,35 @@ def affine_act(x, scale=None, shift=None, relu=False, out=None, mean=None):
     return y
 
 
+def affine_add_act(x, residual, scale=None, shift=None, relu=True, mean=None, out=None):
+    C = x.shape[-1]
+    P = x.numel() // C
+    y = out if out is not None else torch.empty_like(x)
+    N.check(N.lib().fpd_affine_add_act(_p(x), _p(mean), _p(scale), _p(shift), _p(residual), int(relu), _p(y), P, C,
+                                       _stream()), "affine_add_act")
+    return y
+
+
+def fuse_sum(terms, shifts, relu=True, out=None):
+    """out = relu?(sum_j nearest-upsample_{2^shift_j}(terms[j])); terms[j] is [B, H>>s, W>>s, C]."""
+    n = len(terms)
+    B, C = terms[0].shape[0], terms[0].shape[-1]
+    H, W = terms[0].shape[1] << shifts[0], terms[0].shape[2] << shifts[0]
+    y = out if out is not None else torch.empty((B, H, W, C), dtype=torch.float32, device=terms[0].device)
+    arr = (ctypes.c_void_p * n)(*[t.data_ptr() for t in terms])
+    sh = (ctypes.c_int * n)(*[int(s) for s in shifts])
+    N.check(N.lib().fpd_fuse_sum(arr, sh, n, int(relu), _p(y), B, H, W, C, _stream()), "fuse_sum")
+    return y
+
+
+def upsample_bwd(dout, shift, out=None):
+    B, H, W, C = dout.shape
+    d = out if out is not None else torch.empty((B, H >> shift, W >> shift, C), dtype=torch.float32,
+                                                device=dout.device)
+    N.check(N.lib().fpd_upsample_bwd(_p(dout), _p(d), int(shift), B, H, W, C, _stream()), "upsample_bwd")
+    return d
+
+
 def conv2d_tc(a_hi, a_lo, w_hi, w_lo, ksize, bias=None, residual=None, relu_mask=None, out=None, out_scale=1.0):
     B, H, W, Cin = a_hi.shape
     Cout = w_hi.shape[1]

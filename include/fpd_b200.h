@@ -105,6 +105,15 @@ int fpd_affine_act_split(const float* x, const float* mean, const float* scale, 
 /* y = relu?((x-mean)*scale+shift) in full fp32 (materialised activations: stem output, fc output) */
 int fpd_affine_act(const float* x, const float* mean, const float* scale, const float* shift, int relu, float* y,
                    int64_t P, int C, fpd_stream_t stream);
+/* HRNet glue (lib/models/pose_hrnet.py:41-57,78-98 block tails; :256-263 multi-resolution fuse):
+ * y = relu?((x-mean)*scale+shift + residual);  out = relu?(sum_j nearest_up_{2^shift_j}(term_j)) with
+ * terms_host/shifts_host HOST arrays of n<=4 device pointers / log2 factors, summed in order;
+ * dlow = (2^shift)^2 block sums of dout[B,H,W,C]. */
+int fpd_affine_add_act(const float* x, const float* mean, const float* scale, const float* shift,
+                       const float* residual, int relu, float* y, int64_t P, int C, fpd_stream_t stream);
+int fpd_fuse_sum(const float* const* terms_host, const int* shifts_host, int n, int relu, float* out, int B, int H,
+                 int W, int C, fpd_stream_t stream);
+int fpd_upsample_bwd(const float* dout, float* dlow, int shift, int B, int H, int W, int C, fpd_stream_t stream);
 size_t fpd_channel_reduce_workspace_bytes(int64_t P, int C);
 int fpd_channel_sum(const float* dy, int64_t P, int C, float scale, float* out, void* workspace,
                     size_t workspace_bytes, fpd_stream_t stream);

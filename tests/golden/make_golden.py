@@ -162,6 +162,59 @@ def main():
     np.savez_compressed(os.path.join(OUT, "decode.npz"), hm=hm, hm_flipped_raw=hf, flip_back=fb, merged=merged,
                         preds=preds, maxvals=maxvals, merged_preds=mp, merged_maxvals=mv, dets=dets, nms_keep=keep,
                         nms_thresh=np.float32(0.6))
+    # ---- 5. HRNet (lib/models/pose_hrnet.py) small config: all structural cases (bottleneck layer1, transitions,
+    #         2/3/4-branch modules, up/down fuse chains, single-output last module), J=17, 128x96 input ----
+    import warnings
+    warnings.simplefilter("ignore")
+    hr = load("ref_pose_hrnet", "lib/models/pose_hrnet.py")
+
+    class Cfg(dict):
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError:
+                raise AttributeError(k)
+
+    def wrap(d):
+        return Cfg({k: wrap(v) for k, v in d.items()}) if isinstance(d, dict) else d
+
+    def stage(nmod, chans):
+        return dict(NUM_MODULES=nmod, NUM_BRANCHES=len(chans), BLOCK='BASIC', NUM_BLOCKS=[1] * len(chans),
+                    NUM_CHANNELS=chans, FUSE_METHOD='SUM')
+    hcfg = wrap(dict(MODEL=dict(NUM_JOINTS=17, INIT_WEIGHTS=False, PRETRAINED='', EXTRA=dict(
+        PRETRAINED_LAYERS=['*'], FINAL_CONV_KERNEL=1, STAGE2=stage(1, [8, 16]), STAGE3=stage(2, [8, 16, 32]),
+        STAGE4=stage(1, [8, 16, 32, 64])))))
+    torch.manual_seed(5)
+    hnet = hr.get_pose_net(hcfg, False)
+    hnet.train()
+    hsd0 = {k: v.clone() for k, v in hnet.state_dict().items()}
+    hx = torch.randn(2, 3, 128, 96)
+    htarget = torch.from_numpy(gaussian_targets(rng, 2, 17, 32, 24))
+    htw = torch.from_numpy((rng.rand(2, 17, 1) > 0.2).astype(np.float32))
+    hout = hnet(hx)
+    hloss = crit(hout, htarget, htw)
+    hnet.zero_grad()
+    hloss.backward()
+    save = {"x": hx.numpy(), "target": htarget.numpy(), "target_weight": htw.numpy(), "out_train": hout.detach().numpy(),
+            "loss": np.float32(hloss.item())}
+    for k, v in hsd0.items():
+        save["sd/" + k] = v.numpy()
+    names, norms = [], []
+    for k, p in hnet.named_parameters():
+        names.append(k)
+        norms.append(float(p.grad.double().norm()))
+    save["grad_names"] = np.array(names)
+    save["grad_norms"] = np.array(norms, np.float64)
+    for k in ("conv1.weight", "layer1.0.downsample.0.weight", "transition1.1.0.0.weight",
+              "stage3.1.fuse_layers.2.0.1.0.weight", "stage3.0.fuse_layers.0.2.1.weight",
+              "stage4.0.branches.3.0.bn2.bias", "final_layer.bias"):
+        save["grad/" + k] = dict(hnet.named_parameters())[k].grad.numpy()
+    hnet.load_state_dict(hsd0)
+    hnet.eval()
+    with torch.no_grad():
+        save["out_eval"] = hnet(hx).numpy()
+    np.savez_compressed(os.path.join(OUT, "hrnet_small.npz"), **save)
+
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

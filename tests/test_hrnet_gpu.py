@@ -1,0 +1,113 @@
+"""GPU parity of the drop-in HRNet (engine_hrnet + libfpd_b200) against the reference golden vectors (small config
+covering every structural case) and the oracle at the real w32 / w48 widths (BASELINE configs[3] shapes)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-3
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLD, name), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def _sd(gold, prefix="sd/"):
+    return {k[len(prefix):]: torch.from_numpy(v.copy()) for k, v in gold.items() if k.startswith(prefix)}
+
+
+def _rel(a, b):
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+class Cfg(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+
+def wrap(d):
+    return Cfg({k: wrap(v) for k, v in d.items()}) if isinstance(d, dict) else d
+
+
+def stage(nmod, chans, blocks):
+    return dict(NUM_MODULES=nmod, NUM_BRANCHES=len(chans), BLOCK='BASIC', NUM_BLOCKS=[blocks] * len(chans),
+                NUM_CHANNELS=chans, FUSE_METHOD='SUM')
+
+
+def hr_cfg(kind):
+    if kind == "small":
+        st = (stage(1, [8, 16], 1), stage(2, [8, 16, 32], 1), stage(1, [8, 16, 32, 64], 1))
+    else:  # experiments/fpd_coco/hrnet/w32|w48_256x192_adam_lr1e-3.yaml
+        w = 32 if kind == "w32" else 48
+        st = (stage(1, [w, 2 * w], 4), stage(4, [w, 2 * w, 4 * w], 4), stage(3, [w, 2 * w, 4 * w, 8 * w], 4))
+    return wrap(dict(MODEL=dict(NUM_JOINTS=17, INIT_WEIGHTS=False, PRETRAINED='', EXTRA=dict(
+        PRETRAINED_LAYERS=['*'], FINAL_CONV_KERNEL=1, STAGE2=st[0], STAGE3=st[1], STAGE4=st[2]))))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _fp32_reference_mode():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _net(kind, sd=None):
+    import fpd_b200  # noqa: F401
+    from fpd_b200.lib.models import pose_hrnet as H
+    net = H.get_pose_net(hr_cfg(kind), is_train=False)
+    if sd is not None:
+        net.load_state_dict(sd, strict=True)
+    return net.cuda()
+
+
+def test_hrnet_small_matches_reference_golden():
+    from fpd_b200.lib.core.loss import JointsMSELoss
+    g = _load("hrnet_small.npz")
+    net = _net("small", _sd(g))
+    x = torch.from_numpy(g["x"]).cuda()
+    net.eval()
+    with torch.no_grad():
+        out_eval = net(x)
+    assert torch.is_tensor(out_eval) and tuple(out_eval.shape) == g["out_eval"].shape
+    assert _rel(out_eval, g["out_eval"]) < TOL
+    net.train()
+    out = net(x)
+    assert _rel(out.detach(), g["out_train"]) < TOL
+    loss = JointsMSELoss(True)(out, torch.from_numpy(g["target"]).cuda(), torch.from_numpy(g["target_weight"]).cuda())
+    assert abs(loss.item() - float(g["loss"])) < TOL * abs(float(g["loss"]))
+    loss.backward()
+    named = dict(net.named_parameters())
+    for k in [k[5:] for k in g if k.startswith("grad/")]:
+        assert _rel(named[k].grad, g["grad/" + k]) < 5e-3, k
+    norms = dict(zip(g["grad_names"].tolist(), g["grad_norms"].tolist()))
+    for k, p in named.items():
+        n = p.grad.double().norm().item()
+        assert abs(n - norms[k]) < 5e-3 * norms[k] + 1e-12, (k, n, norms[k])
+
+
+@pytest.mark.parametrize("kind,B,training", [("w32", 2, True), ("w32", 2, False), ("w48", 2, False)])
+def test_hrnet_forward_matches_oracle_at_baseline_widths(kind, B, training):
+    from oracle import hrnet_oracle as HO
+    torch.manual_seed(0)
+    net = _net(kind)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+    net.train(training)
+    x = torch.randn(B, 3, 256, 192, device="cuda")
+    sd = HO.annotate_strides({k: v.clone() for k, v in net.state_dict().items()})
+    with torch.no_grad():
+        ref = HO.hrnet(sd, x, training=training)
+        got = net(x)
+    assert tuple(got.shape) == (B, 17, 64, 48)
+    assert _rel(got, ref) < TOL, "rel %.3e" % _rel(got, ref)

@@ -52,6 +52,9 @@ CONV_TC_SHAPES = [
     (1, 32, 32, 128, 128, 3),  # teacher 3x3
     (2, 64, 48, 32, 32, 3),    # HRNet resolution (W not a power of two)
     (2, 16, 12, 128, 128, 3),
+    (2, 64, 64, 16, 128, 1),   # score_ conv: 16 input channels, k-block completed by TMA zero fill
+    (2, 32, 24, 48, 96, 3),    # HRNet-w48 widths
+    (2, 16, 12, 96, 48, 1),
 ]
 
 
@@ -106,6 +109,11 @@ WGRAD_TC_SHAPES = [
     (1, 32, 32, 128, 128, 3),
     (2, 64, 48, 32, 32, 3),
     (2, 32, 32, 128, 256, 1),
+    (2, 64, 64, 128, 16, 1),    # score conv (dY has 16 channels: M tile completed by TMA zero fill)
+    (2, 64, 64, 16, 128, 1),    # score_ conv
+    (2, 128, 128, 32, 64, 1),   # layer1 conv3 / downsample
+    (2, 128, 128, 32, 32, 1),
+    (2, 32, 24, 64, 64, 1),
 ]
 
 

@@ -136,3 +136,58 @@ def test_dropin_module_state_dict_matches_reference_keys(train_gold):
     net.load_state_dict(gold_sd, strict=True)
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         net(torch.zeros(1, 3, 64, 64))
+
+
+# ---------------------------------------------------------------------------------------------- HRNet
+def _hr_cfg():
+    class Cfg(dict):
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError:
+                raise AttributeError(k)
+
+    def wrap(d):
+        return Cfg({k: wrap(v) for k, v in d.items()}) if isinstance(d, dict) else d
+
+    def stage(nmod, chans):
+        return dict(NUM_MODULES=nmod, NUM_BRANCHES=len(chans), BLOCK='BASIC', NUM_BLOCKS=[1] * len(chans),
+                    NUM_CHANNELS=chans, FUSE_METHOD='SUM')
+    return wrap(dict(MODEL=dict(NUM_JOINTS=17, INIT_WEIGHTS=False, PRETRAINED='', EXTRA=dict(
+        PRETRAINED_LAYERS=['*'], FINAL_CONV_KERNEL=1, STAGE2=stage(1, [8, 16]), STAGE3=stage(2, [8, 16, 32]),
+        STAGE4=stage(1, [8, 16, 32, 64])))))
+
+
+def test_hrnet_oracle_matches_reference_golden():
+    from oracle import hrnet_oracle as HO
+    torch.set_num_threads(4)
+    g = _load("hrnet_small.npz")
+    sd = _sd(g)
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.dtype == torch.float32 and "running" not in k}
+    sd.update(params)
+    sda = HO.annotate_strides(sd)
+    x = torch.from_numpy(g["x"])
+    out = HO.hrnet(sda, x, training=True)
+    assert _rel(out.detach(), g["out_train"]) < 2e-5
+    loss = O.joints_mse(out, torch.from_numpy(g["target"]), torch.from_numpy(g["target_weight"]))
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    for k in [k[5:] for k in g if k.startswith("grad/")]:
+        assert _rel(params[k].grad, g["grad/" + k]) < 2e-3, k
+    sd_eval = HO.annotate_strides(_sd(g))
+    with torch.no_grad():
+        assert _rel(HO.hrnet(sd_eval, x, training=False), g["out_eval"]) < 2e-5
+
+
+def test_hrnet_dropin_state_dict_matches_reference_keys():
+    import fpd_b200  # noqa: F401
+    from fpd_b200.lib.models import pose_hrnet as H
+    g = _load("hrnet_small.npz")
+    net = H.get_pose_net(_hr_cfg(), is_train=False)
+    gold_sd = _sd(g)
+    own = net.state_dict()
+    assert list(own.keys()) == list(gold_sd.keys())
+    assert all(own[k].shape == gold_sd[k].shape for k in own)
+    net.load_state_dict(gold_sd, strict=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        net(torch.zeros(1, 3, 64, 64))
