@@ -721,8 +721,30 @@ static int run_channel_reduce(F f, int64_t P, int C, float scale, float* out, vo
   return FPD_OK;
 }
 
+// channel counts that are not a multiple of 4 (the 17-joint HRNet head): one CTA per channel, fixed-order tree
+__global__ void channel_sum_generic_kernel(const float* __restrict__ dy, int64_t P, int C, float scale,
+                                           float* __restrict__ out) {
+  const int c = blockIdx.x;
+  double s = 0.0;
+  for (int64_t r = threadIdx.x; r < P; r += blockDim.x) s += (double)__ldg(dy + r * C + c);
+  __shared__ double red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    out[c] = (float)(t * (double)scale);
+  }
+}
+
 int channel_sum(const float* dy, int64_t P, int C, float scale, float* out, void* workspace, size_t ws_bytes,
                 cudaStream_t stream) {
+  if (C % 4 != 0) {
+    channel_sum_generic_kernel<<<C, 256, 0, stream>>>(dy, P, C, scale, out);
+    FPD_LAUNCH_CHECK();
+    return FPD_OK;
+  }
   SumFunctor f{dy, C};
   return run_channel_reduce<1>(f, P, C, scale, out, workspace, ws_bytes, stream);
 }

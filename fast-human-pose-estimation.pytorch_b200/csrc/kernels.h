@@ -13,6 +13,12 @@ int conv_tc_launch(const float* a_hi, const float* a_lo, const float* w_hi, cons
                    const float* residual, const float* relu_mask, float* y, float out_scale, int B, int H, int W,
                    int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream);
 
+// ---- conv_tc2.cu : same GEMM with BN-apply + ReLU + tf32 split fused into the pipeline (raw fp32 x in) ----
+int conv_tc_fused_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
+                         int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
+                         const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
+                         int ksize, int num_sms, cudaStream_t stream);
+
 // ---- wgrad_tc.cu : tcgen05 weight-gradient GEMM (K = pixels) ----
 bool wgrad_tc_supported(int Cin, int Cout, int ksize);
 size_t wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize, int num_sms);

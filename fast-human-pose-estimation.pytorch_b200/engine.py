@@ -15,6 +15,11 @@ import torch
 from . import ops
 
 
+# conv(relu(bn(x))) with the operand transform inside the tensor-core kernel (csrc/conv_tc2.cu); FPD_FUSED=0 falls back to
+# the two-kernel form (affine_act_split + conv_tc), kept for A/B measurements.
+FUSED_OPERAND_TRANSFORM = os.environ.get("FPD_FUSED", "1") != "0"
+
+
 def precision_passes():
     """3 = 3xTF32 (fp32-grade, the parity mode and the default), 1 = single-pass TF32."""
     mode = os.environ.get("FPD_PRECISION", "tf32x3").lower()
@@ -208,15 +213,20 @@ class Engine:
         res = residual.data if residual is not None else None
         a_hi = a_lo = None
         if c.tc_fwd:
-            a_hi, a_lo = ops.affine_act_split(x.data, scale, shift, relu, split=split, mean=mean)
             w_hi, w_lo = ctx.weights.fwd[conv_name]
-            y = ops.conv2d_tc(a_hi, a_lo, w_hi, w_lo, c.k, bias=bias, residual=res)
+            if FUSED_OPERAND_TRANSFORM:
+                # BN-apply + ReLU + tf32 split happen inside the conv kernel (no separate HBM pass)
+                y = ops.conv2d_tc_fused(x.data, w_hi, w_lo, c.k, mean=mean, scale=scale, shift=shift, relu=relu,
+                                        bias=bias, residual=res)
+            else:
+                a_hi, a_lo = ops.affine_act_split(x.data, scale, shift, relu, split=split, mean=mean)
+                y = ops.conv2d_tc(a_hi, a_lo, w_hi, w_lo, c.k, bias=bias, residual=res)
         else:
             a = ops.affine_act(x.data, scale, shift, relu, mean=mean) if bn_name is not None else x.data
             y = ops.conv2d_simt_fwd(a, c.weight.detach(), bias=bias, residual=res, stride=c.stride, pad=c.pad)
         out = Var(y)
         if ctx.tape is not None:
-            keep_hi, keep_lo = (a_hi, a_lo) if c.tc_wgrad else (None, None)
+            keep = [a_hi, a_lo] if c.tc_wgrad else [None, None]
 
             def bwd():
                 dy = out.grad
@@ -231,7 +241,10 @@ class Engine:
                     dy_hi, dy_lo = ops.affine_act_split(dy, split=split)
                 # ---- weight gradient
                 if c.tc_wgrad:
-                    ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc(keep_hi, keep_lo, dy_hi, dy_lo, c.k)
+                    if keep[0] is None:  # fused forward did not materialise the operand pair: make it now
+                        keep[0], keep[1] = ops.affine_act_split(x.data, scale, shift, relu, split=split, mean=mean)
+                    ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc(keep[0], keep[1], dy_hi, dy_lo, c.k)
+                    keep[0] = keep[1] = None
                 else:
                     a_full = (ops.affine_act(x.data, scale, shift, relu, mean=mean) if bn_name is not None
                               else x.data)

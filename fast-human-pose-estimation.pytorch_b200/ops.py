@@ -116,6 +116,18 @@ def conv2d_tc(a_hi, a_lo, w_hi, w_lo, ksize, bias=None, residual=None, relu_mask
     return y
 
 
+def conv2d_tc_fused(x, w_hi, w_lo, ksize, mean=None, scale=None, shift=None, relu=False, bias=None, residual=None,
+                    relu_mask=None, out=None, out_scale=1.0):
+    """y = conv(relu?((x-mean)*scale+shift)) with the operand transform done inside the kernel (raw fp32 x in)."""
+    B, H, W, Cin = x.shape
+    Cout = w_hi.shape[1]
+    y = out if out is not None else torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
+    N.check(N.lib().fpd_conv2d_tc_fused(_p(x), _p(mean), _p(scale), _p(shift), int(relu), _p(w_hi), _p(w_lo), _p(bias),
+                                        _p(residual), _p(relu_mask), _p(y), float(out_scale), B, H, W, Cin, Cout,
+                                        ksize, _stream()), "conv2d_tc_fused")
+    return y
+
+
 def conv2d_simt_fwd(x, w_oihw, bias=None, residual=None, stride=1, pad=0, out=None):
     B, H, W, Cin = x.shape
     Cout, _, k, _ = w_oihw.shape

@@ -61,6 +61,15 @@ int fpd_conv2d_tc(const float* a_hi, const float* a_lo, const float* w_hi, const
                   const float* residual, const float* relu_mask, float* y, float out_scale, int B, int H, int W,
                   int Cin, int Cout, int ksize, fpd_stream_t stream);
 
+/* Same convolution with the operand preparation fused in: x is the RAW fp32 NHWC activation and the kernel applies
+ * a = relu?((x - pre_mean) * pre_scale + pre_shift) (pre_scale/pre_shift NULL = identity, pre_mean NULL = 0) and the
+ * tf32 hi/lo split in shared memory -- i.e. conv(relu(bn(x))) of lib/models/hourglass.py:34-44 in one kernel.
+ * w_lo NULL => single-pass TF32. Other arguments as fpd_conv2d_tc. */
+int fpd_conv2d_tc_fused(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
+                        int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
+                        const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
+                        int ksize, fpd_stream_t stream);
+
 /* Tensor-core weight gradient: dw_oihw[Cout,Cin,k,k] = scale * sum_pixels dy (x) a(tap-shifted). */
 int fpd_conv2d_wgrad_tc_supported(int Cin, int Cout, int ksize);
 size_t fpd_conv2d_wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize);

@@ -77,6 +77,34 @@ def test_conv2d_tc_forward(shape, passes):
     assert err < (2e-5 if passes == 3 else 3e-3), "conv_tc %s passes=%d rel err %.3e" % (shape, passes, err)
 
 
+@pytest.mark.parametrize("shape", CONV_TC_SHAPES)
+@pytest.mark.parametrize("passes", [3, 1])
+def test_conv2d_tc_fused_bn_relu(shape, passes):
+    """conv(relu(bn_affine(x))) with the operand transform inside the kernel vs torch fp32."""
+    B, H, W, Cin, Cout, k = shape
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g) * 2 + 0.5
+    mean = torch.randn(Cin, device="cuda", generator=g)
+    scale = torch.rand(Cin, device="cuda", generator=g) + 0.5
+    shift = torch.randn(Cin, device="cuda", generator=g) * 0.5
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * (1.0 / (Cin * k * k) ** 0.5)
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(B, Cout, H, W, device="cuda", generator=g)
+    a = F.relu((x - mean.view(1, -1, 1, 1)) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    ref = F.conv2d(a, w, bias, padding=k // 2) + res
+    w_hi, w_lo = o.weight_prep(w, split=(passes == 3))
+    y = o.conv2d_tc_fused(nhwc(x), w_hi, w_lo, k, mean=mean, scale=scale, shift=shift, relu=True, bias=bias,
+                          residual=nhwc(res))
+    # identity pre-op (raw operand, e.g. dgrad on dY)
+    y2 = o.conv2d_tc_fused(nhwc(x), w_hi, w_lo, k)
+    ref2 = F.conv2d(x, w, None, padding=k // 2)
+    torch.cuda.synchronize()
+    tol = 2e-5 if passes == 3 else 3e-3
+    assert relerr(nchw(y), ref) < tol, "fused %s passes=%d rel err %.3e" % (shape, passes, relerr(nchw(y), ref))
+    assert relerr(nchw(y2), ref2) < tol
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 64, 64, 64, 3), (2, 32, 32, 128, 64, 1), (4, 8, 8, 64, 128, 1)])
 def test_conv2d_tc_dgrad_with_relu_mask(shape):
     B, H, W, Cin, Cout, k = shape

@@ -1,0 +1,45 @@
+"""Run one libfpd_b200 kernel shape a few times (for `ncu --set full` captures of the hot kernels).
+
+    ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 2 -c 2 \
+        -o gpurun_out/prof_conv_tc python tools/profile_kernel.py conv 32 64 64 128 128 3
+    ncu --set full ... -k regex:wgrad_tc_kernel ... python tools/profile_kernel.py wgrad 32 64 64 64 64 3
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import fpd_b200  # noqa: F401
+    from fpd_b200 import ops
+    kind = sys.argv[1]
+    B, H, W, Cin, Cout, k = map(int, sys.argv[2:8])
+    iters = int(sys.argv[8]) if len(sys.argv) > 8 else 4
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * 0.03
+    a_hi, a_lo = ops.affine_act_split(x)
+    if kind == "conv":
+        w_hi, w_lo = ops.weight_prep(w)
+        y = torch.empty(B, H, W, Cout, device="cuda")
+        for _ in range(iters):
+            ops.conv2d_tc(a_hi, a_lo, w_hi, w_lo, k, out=y)
+    elif kind == "wgrad":
+        dy = torch.randn(B, H, W, Cout, device="cuda", generator=g)
+        g_hi, g_lo = ops.affine_act_split(dy)
+        for _ in range(iters):
+            ops.conv2d_wgrad_tc(a_hi, a_lo, g_hi, g_lo, k)
+    elif kind == "split":
+        for _ in range(iters):
+            ops.affine_act_split(x, out_hi=a_hi, out_lo=a_lo)
+    else:
+        raise SystemExit("unknown kind " + kind)
+    torch.cuda.synchronize()
+
+
+if __name__ == "__main__":
+    main()
