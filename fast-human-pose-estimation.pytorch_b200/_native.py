@@ -30,6 +30,8 @@ _SIGNATURES = {
     "fpd_conv2d_wgrad_tc_supported": (c_int, [c_int, c_int, c_int]),
     "fpd_conv2d_wgrad_tc_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "fpd_conv2d_wgrad_tc": (c_int, [P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),
+    "fpd_conv2d_wgrad_tc_fused": (c_int, [P, P, P, P, c_int, P, c_int, P, c_float, c_int, c_int, c_int, c_int, c_int,
+                                          c_int, P, c_size_t, P]),
     "fpd_conv2d_simt_fwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "fpd_conv2d_simt_dgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "fpd_conv2d_simt_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
@@ -44,6 +46,7 @@ _SIGNATURES = {
     "fpd_affine_add_act": (c_int, [P, P, P, P, P, c_int, P, c_int64, c_int, P]),
     "fpd_fuse_sum": (c_int, [POINTER(c_void_p), POINTER(c_int), c_int, c_int, P, c_int, c_int, c_int, c_int, P]),
     "fpd_upsample_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "fpd_im2col": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "fpd_channel_reduce_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "fpd_channel_sum": (c_int, [P, c_int64, c_int, c_float, P, P, c_size_t, P]),
     "fpd_bn_bwd_reduce": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int, P, P, c_size_t, P]),

@@ -112,6 +112,14 @@ int fpd_conv2d_wgrad_tc(const float* a_hi, const float* a_lo, const float* dy_hi
                          workspace_bytes, device_sm_count(), S(stream));
 }
 
+int fpd_conv2d_wgrad_tc_fused(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
+                              int pre_relu, const float* dy, int passes, float* dw_oihw, float scale, int B, int H,
+                              int W, int Cin, int Cout, int ksize, void* workspace, size_t workspace_bytes,
+                              fpd_stream_t stream) {
+  return wgrad_tc_fused_launch(x, pre_mean, pre_scale, pre_shift, pre_relu, dy, passes, dw_oihw, scale, B, H, W, Cin,
+                               Cout, ksize, workspace, workspace_bytes, device_sm_count(), S(stream));
+}
+
 int fpd_conv2d_simt_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, int B,
                         int H, int W, int Cin, int Cout, int k, int stride, int pad, fpd_stream_t stream) {
   return conv_simt_fwd(x, w, bias, residual, y, B, H, W, Cin, Cout, k, stride, pad, S(stream));
@@ -162,6 +170,10 @@ int fpd_fuse_sum(const float* const* terms_host, const int* shifts_host, int n, 
 }
 int fpd_upsample_bwd(const float* dout, float* dlow, int shift, int B, int H, int W, int C, fpd_stream_t stream) {
   return upsample_bwd(dout, dlow, shift, B, H, W, C, S(stream));
+}
+int fpd_im2col(const float* x, float* cols, int B, int H, int W, int Cin, int k, int stride, int pad, int Kpad,
+               fpd_stream_t stream) {
+  return im2col(x, cols, B, H, W, Cin, k, stride, pad, Kpad, S(stream));
 }
 size_t fpd_channel_reduce_workspace_bytes(int64_t P, int C) { return channel_reduce_workspace_bytes(P, C); }
 int fpd_channel_sum(const float* dy, int64_t P, int C, float scale, float* out, void* ws, size_t wsb,

@@ -565,6 +565,38 @@ __global__ void upsample_bwd_kernel(const float4* __restrict__ dout, float4* __r
   }
 }
 
+
+// ---- im2col for the few-input-channel stem convs (hourglass 7x7 s2, reference hourglass.py:116; HRNet 3x3 s2,
+//      pose_hrnet.py:281): cols[b,ho,wo, (kh*k+kw)*Cin + ci] = x[b, ho*s+kh-p, wo*s+kw-p, ci], zero outside the image and
+//      for the K padding. The result is an ordinary NHWC tensor with Kpad channels, so the stem becomes a 1x1
+//      convolution on the tensor-core path (forward and weight gradient).
+__global__ void im2col_kernel(const float* __restrict__ x, float4* __restrict__ cols, int B, int H, int W, int Cin,
+                              int k, int stride, int pad, int Ho, int Wo, int Kpad) {
+  const int K = k * k * Cin;
+  const int kq = Kpad / 4;
+  const int64_t n = (int64_t)B * Ho * Wo * kq;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k4 = (int)(i % kq) * 4;
+    int64_t t = i / kq;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kk = k4 + j;
+      float val = 0.f;
+      if (kk < K) {
+        const int ci = kk % Cin, tap = kk / Cin;
+        const int hi = ho * stride + tap / k - pad, wi = wo * stride + tap % k - pad;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) val = __ldg(x + (((int64_t)b * H + hi) * W + wi) * Cin + ci);
+      }
+      v[j] = val;
+    }
+    cols[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 inline int grid_for(int64_t n, int threads) {
   int64_t b = (n + threads - 1) / threads;
   const int64_t cap = 148 * 16;
@@ -822,6 +854,16 @@ int upsample_bwd(const float* dout, float* dlow, int shift, int B, int H, int W,
   const int Ho = H >> shift, Wo = W >> shift;
   const int64_t n = (int64_t)B * Ho * Wo * (C / 4);
   upsample_bwd_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const float4*)dout, (float4*)dlow, shift, B, Ho, Wo, C / 4);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int im2col(const float* x, float* cols, int B, int H, int W, int Cin, int k, int stride, int pad, int Kpad,
+           cudaStream_t stream) {
+  FPD_REQUIRE(Kpad % 4 == 0 && Kpad >= k * k * Cin, "im2col: Kpad=%d must be a multiple of 4 and >= k*k*Cin", Kpad);
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const int64_t n = (int64_t)B * Ho * Wo * (Kpad / 4);
+  im2col_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, (float4*)cols, B, H, W, Cin, k, stride, pad, Ho, Wo, Kpad);
   FPD_LAUNCH_CHECK();
   return FPD_OK;
 }

@@ -26,6 +26,12 @@ int wgrad_tc_launch(const float* a_hi, const float* a_lo, const float* dy_hi, co
                     float scale, int B, int H, int W, int Cin, int Cout, int ksize, void* workspace,
                     size_t workspace_bytes, int num_sms, cudaStream_t stream);
 
+// ---- wgrad_tc2.cu : same GEMM reading RAW x and dY; BN-apply + ReLU + tf32 split fused into the pipeline ----
+int wgrad_tc_fused_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
+                          int pre_relu, const float* dy, int passes, float* dw_oihw, float scale, int B, int H, int W,
+                          int Cin, int Cout, int ksize, void* workspace, size_t workspace_bytes, int num_sms,
+                          cudaStream_t stream);
+
 // ---- conv_simt.cu : generic fp32 CUDA-core convolution (any k / stride / pad, NHWC activations,
 //      OIHW weights). Used for the shapes the tensor-core kernels do not take (7x7 stem, 16-channel
 //      score convs) and as the on-device cross-check in tests. ----
@@ -60,6 +66,9 @@ int fuse_sum(const float* const* terms, const int* shifts, int n, int relu, floa
              cudaStream_t stream);
 // dlow = sum over (2^shift)^2 blocks of dout [B,H,W,C]
 int upsample_bwd(const float* dout, float* dlow, int shift, int B, int H, int W, int C, cudaStream_t stream);
+// cols[B,Ho,Wo,Kpad] = im2col(x[B,H,W,Cin]) with K index (kh*k+kw)*Cin+ci, zero padded to Kpad channels
+int im2col(const float* x, float* cols, int B, int H, int W, int Cin, int k, int stride, int pad, int Kpad,
+           cudaStream_t stream);
 int maxpool2x2_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream);
 int maxpool2x2_bwd(const float* x, const float* dy, float* dx, int accumulate, int B, int H, int W, int C,
                    cudaStream_t stream);

@@ -17,7 +17,10 @@ from . import ops
 
 # conv(relu(bn(x))) with the operand transform inside the tensor-core kernel (csrc/conv_tc2.cu); FPD_FUSED=0 falls back to
 # the two-kernel form (affine_act_split + conv_tc), kept for A/B measurements.
-FUSED_OPERAND_TRANSFORM = os.environ.get("FPD_FUSED", "1") != "0"
+_FUSED = os.environ.get("FPD_FUSED", "1").lower()
+FUSED_FWD = _FUSED in ("1", "all", "fwd")     # forward convs (student + teacher)
+FUSED_DGRAD = _FUSED in ("1", "all", "bwd", "dgrad")
+FUSED_WGRAD = _FUSED in ("1", "all", "bwd", "wgrad")
 
 
 def precision_passes():
@@ -73,6 +76,14 @@ class ConvRef:
         self.cout = mod.out_channels
 
     @property
+    def im2col_kpad(self):
+        """Few-input-channel stem convs run as im2col + 1x1 tensor-core conv; returns the padded K or 0."""
+        K = self.cin * self.k * self.k
+        if self.cin < 4 and self.k > 1 and K <= 256 and self.cout % 16 == 0 and self.cout <= 256:
+            return (K + 31) // 32 * 32
+        return 0
+
+    @property
     def tc_fwd(self):
         return self.stride == 1 and self.pad == self.k // 2 and ops.conv2d_tc_supported(self.cin, self.cout, self.k)
 
@@ -103,6 +114,13 @@ class PreparedWeights:
         split = passes == 3
         for c in convs:
             w = c.weight.detach()
+            kpad = c.im2col_kpad
+            if kpad:
+                # OIHW -> [Cout][(kh,kw,ci)] zero-padded to kpad, as a 1x1 conv weight
+                w2 = torch.zeros((c.cout, kpad, 1, 1), dtype=torch.float32, device=w.device)
+                w2[:, :c.cin * c.k * c.k, 0, 0] = w.permute(0, 2, 3, 1).reshape(c.cout, -1)
+                self.fwd[c.name] = ops.weight_prep(w2, for_dgrad=False, split=split)
+                continue
             if c.tc_fwd:
                 self.fwd[c.name] = ops.weight_prep(w, for_dgrad=False, split=split)
             if need_dgrad and c.tc_dgrad:
@@ -212,9 +230,31 @@ class Engine:
         bias = c.bias.detach() if c.bias is not None else None
         res = residual.data if residual is not None else None
         a_hi = a_lo = None
+        kpad = c.im2col_kpad if bn_name is None else 0
+        if kpad:
+            cols = ops.im2col(x.data, c.k, c.stride, c.pad, kpad)
+            w_hi, w_lo = ctx.weights.fwd[conv_name]
+            out = Var(ops.conv2d_tc_fused(cols, w_hi, w_lo, 1, bias=bias, residual=res))
+            if ctx.tape is not None:
+                def bwd_stem():
+                    dy = out.grad
+                    if dy is None:
+                        return
+                    if residual is not None:
+                        residual.add_grad(dy, owned=False)
+                    if c.bias is not None:
+                        ctx.pgrads[c.bias] = ops.channel_sum(dy)
+                    dw = ops.conv2d_wgrad_tc_fused(cols, dy, 1, passes=ctx.passes)      # [Cout, kpad, 1, 1]
+                    K = c.cin * c.k * c.k
+                    ctx.pgrads[c.weight] = dw[:, :K, 0, 0].reshape(c.cout, c.k, c.k, c.cin).permute(0, 3, 1, 2).contiguous()
+                    if need_dx:
+                        x.add_grad(ops.conv2d_simt_dgrad(dy, c.weight.detach(), x.data.shape[1:3], stride=c.stride,
+                                                         pad=c.pad), owned=True)
+                ctx.tape.append(bwd_stem)
+            return out
         if c.tc_fwd:
             w_hi, w_lo = ctx.weights.fwd[conv_name]
-            if FUSED_OPERAND_TRANSFORM:
+            if FUSED_FWD:
                 # BN-apply + ReLU + tf32 split happen inside the conv kernel (no separate HBM pass)
                 y = ops.conv2d_tc_fused(x.data, w_hi, w_lo, c.k, mean=mean, scale=scale, shift=shift, relu=relu,
                                         bias=bias, residual=res)
@@ -237,10 +277,13 @@ class Engine:
                 if c.bias is not None:
                     ctx.pgrads[c.bias] = ops.channel_sum(dy)
                 dy_hi = dy_lo = None
-                if c.tc_wgrad or (need_dx and c.tc_dgrad):
+                if (c.tc_wgrad and not FUSED_WGRAD) or (need_dx and c.tc_dgrad and not FUSED_DGRAD):
                     dy_hi, dy_lo = ops.affine_act_split(dy, split=split)
                 # ---- weight gradient
-                if c.tc_wgrad:
+                if c.tc_wgrad and FUSED_WGRAD:
+                    ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc_fused(x.data, dy, c.k, mean=mean, scale=scale, shift=shift,
+                                                                     relu=relu, passes=ctx.passes)
+                elif c.tc_wgrad:
                     if keep[0] is None:  # fused forward did not materialise the operand pair: make it now
                         keep[0], keep[1] = ops.affine_act_split(x.data, scale, shift, relu, split=split, mean=mean)
                     ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc(keep[0], keep[1], dy_hi, dy_lo, c.k)
@@ -254,7 +297,10 @@ class Engine:
                 # ---- data gradient w.r.t. the conv input a = act(bn(x))
                 if c.tc_dgrad:
                     wd_hi, wd_lo = ctx.weights.dgrad[conv_name]
-                    da = ops.conv2d_tc(dy_hi, dy_lo, wd_hi, wd_lo, c.k)
+                    if FUSED_DGRAD:
+                        da = ops.conv2d_tc_fused(dy, wd_hi, wd_lo, c.k)
+                    else:
+                        da = ops.conv2d_tc(dy_hi, dy_lo, wd_hi, wd_lo, c.k)
                 else:
                     da = ops.conv2d_simt_dgrad(dy, c.weight.detach(), x.data.shape[1:3], stride=c.stride, pad=c.pad)
                 if bn_name is not None:

@@ -107,6 +107,15 @@ def upsample_bwd(dout, shift, out=None):
     return d
 
 
+def im2col(x, k, stride, pad, kpad, out=None):
+    B, H, W, Cin = x.shape
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    cols = out if out is not None else torch.empty((B, Ho, Wo, kpad), dtype=torch.float32, device=x.device)
+    N.check(N.lib().fpd_im2col(_p(x), _p(cols), B, H, W, Cin, k, stride, pad, kpad, _stream()), "im2col")
+    return cols
+
+
 def conv2d_tc(a_hi, a_lo, w_hi, w_lo, ksize, bias=None, residual=None, relu_mask=None, out=None, out_scale=1.0):
     B, H, W, Cin = a_hi.shape
     Cout = w_hi.shape[1]
@@ -171,6 +180,20 @@ def conv2d_wgrad_tc(a_hi, a_lo, dy_hi, dy_lo, ksize, scale=1.0, out=None):
     ws = _ws.get(nb, a_hi.device)
     N.check(N.lib().fpd_conv2d_wgrad_tc(_p(a_hi), _p(a_lo), _p(dy_hi), _p(dy_lo), _p(dw), float(scale), B, H, W, Cin,
                                         Cout, ksize, _p(ws), ws.numel(), _stream()), "conv2d_wgrad_tc")
+    return dw
+
+
+def conv2d_wgrad_tc_fused(x, dy, ksize, mean=None, scale=None, shift=None, relu=False, passes=3, out_scale=1.0,
+                          out=None):
+    """dW for y = conv(relu?((x-mean)*scale+shift)) given raw x and raw dy (operand transform inside the kernel)."""
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    dw = out if out is not None else torch.empty((Cout, Cin, ksize, ksize), dtype=torch.float32, device=x.device)
+    nb = N.lib().fpd_conv2d_wgrad_tc_workspace_bytes(B, H, W, Cin, Cout, ksize)
+    ws = _ws.get(nb, x.device)
+    N.check(N.lib().fpd_conv2d_wgrad_tc_fused(_p(x), _p(mean), _p(scale), _p(shift), int(relu), _p(dy), int(passes),
+                                              _p(dw), float(out_scale), B, H, W, Cin, Cout, ksize, _p(ws), ws.numel(),
+                                              _stream()), "conv2d_wgrad_tc_fused")
     return dw
 
 

@@ -77,6 +77,14 @@ int fpd_conv2d_wgrad_tc(const float* a_hi, const float* a_lo, const float* dy_hi
                         float* dw_oihw, float scale, int B, int H, int W, int Cin, int Cout, int ksize,
                         void* workspace, size_t workspace_bytes, fpd_stream_t stream);
 
+/* Weight gradient with the operand preparation fused in: x and dy are RAW fp32 NHWC tensors; the kernel applies
+ * a = relu?((x - pre_mean) * pre_scale + pre_shift) (NULLs = identity), zeroes the 3x3 padding positions and does the
+ * tf32 split on chip. passes = 3 (3xTF32) or 1. Workspace: fpd_conv2d_wgrad_tc_workspace_bytes. */
+int fpd_conv2d_wgrad_tc_fused(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
+                              int pre_relu, const float* dy, int passes, float* dw_oihw, float scale, int B, int H,
+                              int W, int Cin, int Cout, int ksize, void* workspace, size_t workspace_bytes,
+                              fpd_stream_t stream);
+
 /* Generic fp32 CUDA-core convolution (any k/stride/pad): x NHWC [B,H,W,Cin], w OIHW. */
 int fpd_conv2d_simt_fwd(const float* x, const float* w_oihw, const float* bias, const float* residual, float* y,
                         int B, int H, int W, int Cin, int Cout, int k, int stride, int pad, fpd_stream_t stream);
@@ -123,6 +131,11 @@ int fpd_affine_add_act(const float* x, const float* mean, const float* scale, co
 int fpd_fuse_sum(const float* const* terms_host, const int* shifts_host, int n, int relu, float* out, int B, int H,
                  int W, int C, fpd_stream_t stream);
 int fpd_upsample_bwd(const float* dout, float* dlow, int shift, int B, int H, int W, int C, fpd_stream_t stream);
+/* Stem convs with very few input channels (hourglass.py:116 7x7 s2 Cin=3; pose_hrnet.py:281 3x3 s2 Cin=3):
+ * cols[B,Ho,Wo,Kpad] with channel index (kh*k+kw)*Cin+ci (zero outside the image / beyond k*k*Cin), which turns the
+ * stem into a 1x1 convolution for the tensor-core kernels. */
+int fpd_im2col(const float* x, float* cols, int B, int H, int W, int Cin, int k, int stride, int pad, int Kpad,
+               fpd_stream_t stream);
 size_t fpd_channel_reduce_workspace_bytes(int64_t P, int C);
 int fpd_channel_sum(const float* dy, int64_t P, int C, float scale, float* out, void* workspace,
                     size_t workspace_bytes, fpd_stream_t stream);

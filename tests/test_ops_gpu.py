@@ -164,6 +164,31 @@ def test_conv2d_wgrad_tc(shape, passes):
     assert err < (2e-5 if passes == 3 else 3e-3), "wgrad_tc %s passes=%d rel err %.3e" % (shape, passes, err)
 
 
+@pytest.mark.parametrize("shape", WGRAD_TC_SHAPES)
+@pytest.mark.parametrize("passes", [3, 1])
+def test_conv2d_wgrad_tc_fused_bn_relu(shape, passes):
+    """dW of conv(relu(bn_affine(x))) from raw x / raw dy with the operand transform inside the kernel."""
+    B, H, W, Cin, Cout, k = shape
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(99)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g) * 2 + 0.5
+    mean = torch.randn(Cin, device="cuda", generator=g)
+    scale = torch.rand(Cin, device="cuda", generator=g) + 0.5
+    shift = torch.randn(Cin, device="cuda", generator=g) * 0.5
+    a = F.relu((x - mean.view(1, -1, 1, 1)) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    w = torch.zeros(Cout, Cin, k, k, device="cuda", requires_grad=True)
+    dy = torch.randn(B, Cout, H, W, device="cuda", generator=g)
+    (dw_ref,) = torch.autograd.grad(F.conv2d(a, w, None, padding=k // 2), w, dy)
+    dw = o.conv2d_wgrad_tc_fused(nhwc(x), nhwc(dy), k, mean=mean, scale=scale, shift=shift, relu=True, passes=passes)
+    w2 = torch.zeros(Cout, Cin, k, k, device="cuda", requires_grad=True)
+    (dw_ref2,) = torch.autograd.grad(F.conv2d(x, w2, None, padding=k // 2), w2, dy)
+    dw2 = o.conv2d_wgrad_tc_fused(nhwc(x), nhwc(dy), k, passes=passes)
+    torch.cuda.synchronize()
+    tol = 2e-5 if passes == 3 else 3e-3
+    assert relerr(dw, dw_ref) < tol, "wgrad fused %s passes=%d rel err %.3e" % (shape, passes, relerr(dw, dw_ref))
+    assert relerr(dw2, dw_ref2) < tol
+
+
 @pytest.mark.parametrize("cfg", [
     # B, H, W, Cin, Cout, k, stride, pad
     (2, 64, 64, 3, 32, 7, 2, 3),
@@ -397,3 +422,29 @@ def test_adam_flat_matches_torch():
         o.adam_flat(p, gr, m, v, 2.5e-4, 0.9, 0.999, 1e-8, 0.0, step)
     torch.cuda.synchronize()
     assert relerr(p, ref.detach()) < 1e-6
+
+
+@pytest.mark.parametrize("cfg", [(2, 64, 64, 3, 32, 7, 2, 3), (2, 64, 48, 3, 64, 3, 2, 1)])
+def test_stem_im2col_tensor_core_path(cfg):
+    """Stem convs (Cin=3) as im2col + 1x1 tensor-core conv / weight gradient vs torch fp32."""
+    B, H, W, Cin, Cout, k, stride, pad = cfg
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g, requires_grad=True)
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    y_ref = F.conv2d(x, w, bias, stride=stride, padding=pad)
+    dy = torch.randn_like(y_ref)
+    (dw_ref,) = torch.autograd.grad(y_ref, w, dy)
+    K = Cin * k * k
+    kpad = (K + 31) // 32 * 32
+    cols = o.im2col(nhwc(x), k, stride, pad, kpad)
+    w2 = torch.zeros(Cout, kpad, 1, 1, device="cuda")
+    w2[:, :K, 0, 0] = w.detach().permute(0, 2, 3, 1).reshape(Cout, -1)
+    w_hi, w_lo = o.weight_prep(w2)
+    y = o.conv2d_tc_fused(cols, w_hi, w_lo, 1, bias=bias)
+    dw = o.conv2d_wgrad_tc_fused(cols, nhwc(dy), 1)
+    dw = dw[:, :K, 0, 0].reshape(Cout, k, k, Cin).permute(0, 3, 1, 2)
+    torch.cuda.synchronize()
+    assert relerr(nchw(y), y_ref) < 2e-5
+    assert relerr(dw, dw_ref) < 2e-5
