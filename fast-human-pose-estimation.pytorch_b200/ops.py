@@ -4,6 +4,7 @@ Every function takes contiguous fp32 CUDA tensors, enqueues on torch's current s
 (or fills) tensors. Activations are NHWC ([B,H,W,C]) unless a name says otherwise.
 """
 import ctypes
+import os
 
 import torch
 
@@ -125,15 +126,18 @@ def conv2d_tc(a_hi, a_lo, w_hi, w_lo, ksize, bias=None, residual=None, relu_mask
     return y
 
 
+CONV_FUSED_IMPL = os.environ.get("FPD_CONV_IMPL", "ts").lower()   # "ts": A operand in TMEM (conv_tc3.cu); "ss": conv_tc2.cu
+
+
 def conv2d_tc_fused(x, w_hi, w_lo, ksize, mean=None, scale=None, shift=None, relu=False, bias=None, residual=None,
-                    relu_mask=None, out=None, out_scale=1.0):
+                    relu_mask=None, out=None, out_scale=1.0, impl=None):
     """y = conv(relu?((x-mean)*scale+shift)) with the operand transform done inside the kernel (raw fp32 x in)."""
     B, H, W, Cin = x.shape
     Cout = w_hi.shape[1]
     y = out if out is not None else torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
-    N.check(N.lib().fpd_conv2d_tc_fused(_p(x), _p(mean), _p(scale), _p(shift), int(relu), _p(w_hi), _p(w_lo), _p(bias),
-                                        _p(residual), _p(relu_mask), _p(y), float(out_scale), B, H, W, Cin, Cout,
-                                        ksize, _stream()), "conv2d_tc_fused")
+    fn = N.lib().fpd_conv2d_tc_ts if (impl or CONV_FUSED_IMPL) == "ts" else N.lib().fpd_conv2d_tc_fused
+    N.check(fn(_p(x), _p(mean), _p(scale), _p(shift), int(relu), _p(w_hi), _p(w_lo), _p(bias), _p(residual),
+               _p(relu_mask), _p(y), float(out_scale), B, H, W, Cin, Cout, ksize, _stream()), "conv2d_tc_fused")
     return y
 
 

@@ -79,7 +79,8 @@ def test_conv2d_tc_forward(shape, passes):
 
 @pytest.mark.parametrize("shape", CONV_TC_SHAPES)
 @pytest.mark.parametrize("passes", [3, 1])
-def test_conv2d_tc_fused_bn_relu(shape, passes):
+@pytest.mark.parametrize("impl", ["ss", "ts"])
+def test_conv2d_tc_fused_bn_relu(shape, passes, impl):
     """conv(relu(bn_affine(x))) with the operand transform inside the kernel vs torch fp32."""
     B, H, W, Cin, Cout, k = shape
     o = ops()
@@ -95,9 +96,9 @@ def test_conv2d_tc_fused_bn_relu(shape, passes):
     ref = F.conv2d(a, w, bias, padding=k // 2) + res
     w_hi, w_lo = o.weight_prep(w, split=(passes == 3))
     y = o.conv2d_tc_fused(nhwc(x), w_hi, w_lo, k, mean=mean, scale=scale, shift=shift, relu=True, bias=bias,
-                          residual=nhwc(res))
+                          residual=nhwc(res), impl=impl)
     # identity pre-op (raw operand, e.g. dgrad on dY)
-    y2 = o.conv2d_tc_fused(nhwc(x), w_hi, w_lo, k)
+    y2 = o.conv2d_tc_fused(nhwc(x), w_hi, w_lo, k, impl=impl)
     ref2 = F.conv2d(x, w, None, padding=k // 2)
     torch.cuda.synchronize()
     tol = 2e-5 if passes == 3 else 3e-3

@@ -28,6 +28,17 @@ def main():
         y = torch.empty(B, H, W, Cout, device="cuda")
         for _ in range(iters):
             ops.conv2d_tc(a_hi, a_lo, w_hi, w_lo, k, out=y)
+    elif kind in ("conv_fused", "conv_ts"):
+        w_hi, w_lo = ops.weight_prep(w)
+        y = torch.empty(B, H, W, Cout, device="cuda")
+        mean = torch.zeros(Cin, device="cuda"); scale = torch.ones(Cin, device="cuda"); shift = torch.zeros(Cin, device="cuda")
+        for _ in range(iters):
+            ops.conv2d_tc_fused(x, w_hi, w_lo, k, mean=mean, scale=scale, shift=shift, relu=True, out=y,
+                                impl="ts" if kind == "conv_ts" else "ss")
+    elif kind == "wgrad_fused":
+        dy = torch.randn(B, H, W, Cout, device="cuda", generator=g)
+        for _ in range(iters):
+            ops.conv2d_wgrad_tc_fused(x, dy, k, relu=True)
     elif kind == "wgrad":
         dy = torch.randn(B, H, W, Cout, device="cuda", generator=g)
         g_hi, g_lo = ops.affine_act_split(dy)
