@@ -59,6 +59,16 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = to_tf32(x - hi);
 }
 
+// Same split with the rounding done in integer arithmetic (2 ALU ops instead of the multi-instruction emulation ptxas
+// emits for cvt.rna.tf32 on sm_100a): adding half an ulp of the 13 dropped bits and truncating is round-to-nearest,
+// ties away from zero, i.e. exactly cvt.rna for finite inputs. Used inside the tensor-core pipelines where the
+// transform competes with the MMA issue for scheduler slots.
+__device__ __forceinline__ void split_tf32_fast(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  const float r = x - hi;
+  lo = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

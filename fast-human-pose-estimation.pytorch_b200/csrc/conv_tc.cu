@@ -97,7 +97,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int tw = tile % p.tiles_w;
         const int th = (tile / p.tiles_w) % p.tiles_h;
@@ -106,9 +107,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dh = (p.taps == 9) ? (tap / 3 - 1) : 0;
           const int dw = (p.taps == 9) ? (tap % 3 - 1) : 0;
-          for (int cb = 0; cb < kblocks_per_tap; ++cb, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1;
+          for (int cb = 0; cb < kblocks_per_tap; ++cb, s = (s + 1 == p.stages ? 0 : s + 1), ph ^= (s == 0)) {
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* st = smem + (size_t)s * stage_bytes;
             mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
@@ -127,7 +126,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(kTileM, (uint32_t)p.Cout, 0, 0);
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       uint32_t tile_iter = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
         const uint32_t as = tile_iter & 1;
@@ -135,9 +135,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         mbar_wait(&tmem_empty[as], aph ^ 1);
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + as * (uint32_t)p.tmem_cols;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        for (int kb = 0; kb < kblocks; ++kb, s = (s + 1 == p.stages ? 0 : s + 1), ph ^= (s == 0)) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after_sync();
           const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);

@@ -125,7 +125,8 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)(kABytes + (split ? 2 : 1) * p.b_bytes);
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int tw = tile % p.tiles_w;
         const int th = (tile / p.tiles_w) % p.tiles_h;
@@ -134,9 +135,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dh = (p.taps == 9) ? (tap / 3 - 1) : 0;
           const int dw = (p.taps == 9) ? (tap % 3 - 1) : 0;
-          for (int cb = 0; cb < kblocks_per_tap; ++cb, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1;
+          for (int cb = 0; cb < kblocks_per_tap; ++cb, s = (s + 1 == p.stages ? 0 : s + 1), ph ^= (s == 0)) {
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* st = smem + (size_t)s * stage_bytes;
             mbar_expect_tx(&full_bar[s], tx_bytes);
@@ -151,16 +150,16 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(kTileM, (uint32_t)p.Cout, 0, 0);
-      uint32_t it = 0, tile_iter = 0;
+      uint32_t tile_iter = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
-        const uint32_t as = tile_iter % (uint32_t)p.acc_stages;
-        const uint32_t aph = (tile_iter / (uint32_t)p.acc_stages) & 1;
+        const uint32_t as = p.acc_stages == 2 ? (tile_iter & 1) : 0u;
+        const uint32_t aph = (p.acc_stages == 2 ? (tile_iter >> 1) : tile_iter) & 1;
         mbar_wait(&tmem_empty[as], aph ^ 1);
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + as * (uint32_t)p.tmem_cols;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        for (int kb = 0; kb < kblocks; ++kb, s = (s + 1 == p.stages ? 0 : s + 1), ph ^= (s == 0)) {
           mbar_wait(&ready_bar[s], ph);  // A tile is in TMEM (implies the TMA bytes of this stage have landed)
           tc_fence_after_sync();
           const uint32_t b_hi = smem_u32(smem + (size_t)s * stage_bytes) + kABytes;
@@ -190,8 +189,8 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int m = q * 32 + lane;
     uint32_t tile_iter = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
-      const uint32_t as = tile_iter % (uint32_t)p.acc_stages;
-      const uint32_t aph = (tile_iter / (uint32_t)p.acc_stages) & 1;
+      const uint32_t as = p.acc_stages == 2 ? (tile_iter & 1) : 0u;
+      const uint32_t aph = (p.acc_stages == 2 ? (tile_iter >> 1) : tile_iter) & 1;
       const int tw = tile % p.tiles_w;
       const int th = (tile / p.tiles_w) % p.tiles_h;
       const int tn = tile / (p.tiles_w * p.tiles_h);
@@ -252,7 +251,9 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int dn = r / (p.bw * p.bh), dh_ = (r / p.bw) % p.bh, dw_ = r % p.bw;
     const bool has_affine = p.pre_scale != nullptr;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_col0 + (uint32_t)half * 16u;
-    uint32_t it = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t s_mean_a = smem_u32(s_mean), s_scale_a = smem_u32(s_scale), s_shift_a = smem_u32(s_shift);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int tw = tile % p.tiles_w;
       const int th = (tile / p.tiles_w) % p.tiles_h;
@@ -263,9 +264,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const int hh = h_base + ((p.taps == 9) ? (tap / 3 - 1) : 0);
         const int ww = w_base + ((p.taps == 9) ? (tap % 3 - 1) : 0);
         const bool inb = pn < p.B && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;
-        for (int cb = 0; cb < kblocks_per_tap; ++cb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        for (int cb = 0; cb < kblocks_per_tap; ++cb, s = (s + 1 == p.stages ? 0 : s + 1), ph ^= (s == 0)) {
           mbar_wait(&full_bar[s], ph);
           const uint32_t xrow = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)r * 128u;
           uint32_t hi[16], lo[16];
@@ -277,9 +276,9 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             if (inb && c < p.Cin) {
               v = lds128(xrow + (uint32_t)((i ^ (r & 7)) << 4));
               if (has_affine) {
-                const float4 mu = *reinterpret_cast<const float4*>(s_mean + c);
-                const float4 sc = *reinterpret_cast<const float4*>(s_scale + c);
-                const float4 sh = *reinterpret_cast<const float4*>(s_shift + c);
+                const float4 mu = lds128(s_mean_a + (uint32_t)c * 4u);
+                const float4 sc = lds128(s_scale_a + (uint32_t)c * 4u);
+                const float4 sh = lds128(s_shift_a + (uint32_t)c * 4u);
                 v.x = fmaf(v.x - mu.x, sc.x, sh.x); v.y = fmaf(v.y - mu.y, sc.y, sh.y);
                 v.z = fmaf(v.z - mu.z, sc.z, sh.z); v.w = fmaf(v.w - mu.w, sc.w, sh.w);
               }
@@ -288,8 +287,8 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               }
             }
             float4 h, l;
-            split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-            split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+            split_tf32_fast(v.x, h.x, l.x); split_tf32_fast(v.y, h.y, l.y);
+            split_tf32_fast(v.z, h.z, l.z); split_tf32_fast(v.w, h.w, l.w);
             hi[ii * 4 + 0] = __float_as_uint(h.x); hi[ii * 4 + 1] = __float_as_uint(h.y);
             hi[ii * 4 + 2] = __float_as_uint(h.z); hi[ii * 4 + 3] = __float_as_uint(h.w);
             lo[ii * 4 + 0] = __float_as_uint(l.x); lo[ii * 4 + 1] = __float_as_uint(l.y);
