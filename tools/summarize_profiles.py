@@ -1,0 +1,79 @@
+"""Turn the ncu artefacts a gpurun call brought back (gpurun_out/) into the tracked summaries under profiles/.
+
+    python tools/summarize_profiles.py r1      # reads gpurun_out/launches_r1.csv, gpurun_out/prof_*.ncu-rep
+"""
+import collections
+import csv
+import gzip
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+SRC = os.path.join(ROOT, "gpurun_out")
+
+KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum", "sm__inst_executed.avg.per_cycle_elapsed"]
+
+
+def launches(tag):
+    path = os.path.join(SRC, "launches_%s.csv" % tag)
+    if not os.path.exists(path):
+        return
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr, data = rows[hi], rows[hi + 1:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in data:
+        if len(r) < len(hdr):
+            continue
+        name = re.sub(r"\(.*", "", r[ix["Kernel Name"]]).replace("fpd::<unnamed>::", "")
+        agg[name][0] += 1
+        agg[name][1] += float(r[ix["Metric Value"]].replace(",", "")) / 1000.0
+    tot = sum(v[1] for v in agg.values())
+    with open(os.path.join(OUT, "%s_launches_summary.md" % tag), "w") as f:
+        f.write("# %s: ncu launch list of ONE eager FPD training step (B=32, student s4 f128 + teacher s8 f256)\n\n" % tag)
+        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv "
+                "--log-file gpurun_out/launches_%s.csv python tools/profile_step.py --ncu` (cold-cache, serialised: "
+                "compare SHARES, not absolutes). Raw list: `%s_launches.csv.gz`.\n\n" % (tag, tag))
+        f.write("%d kernel launches, %.1f ms summed device time.\n\n| kernel | launches | total us | share |\n|---|---:|---:|---:|\n"
+                % (sum(v[0] for v in agg.values()), tot / 1000.0))
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("| `%s` | %d | %.1f | %.1f %% |\n" % (k[-90:], v[0], v[1], 100 * v[1] / tot))
+    with open(path, "rb") as fi, gzip.open(os.path.join(OUT, "%s_launches.csv.gz" % tag), "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+
+
+def report(tag, name, title):
+    rep = os.path.join(SRC, name + ".ncu-rep")
+    if not os.path.exists(rep):
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    with open(os.path.join(OUT, "%s_%s.md" % (tag, name)), "w") as f:
+        f.write("# %s: `ncu --set full --clock-control none --import-source on` -- %s\n\n" % (tag, title))
+        f.write("| metric | value | unit |\n|---|---:|---|\n")
+        for i, h in enumerate(hdr):
+            base = h.split(".TriageCompute.")[-1]
+            if base in KEYS or h in KEYS:
+                f.write("| `%s` | %s | %s |\n" % (h, vals[i], units[i]))
+
+
+if __name__ == "__main__":
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+    os.makedirs(OUT, exist_ok=True)
+    launches(tag)
+    report(tag, "prof_conv_tc_ss", "conv_tc_kernel (SS, pre-split operands), 3x3 128->128 @64x64, B=32, 3xTF32")
+    report(tag, "prof_conv_tc_ts", "conv_tc_ts_kernel (fused transform, A in TMEM), 3x3 128->128 @64x64, B=32, 3xTF32")
+    print(sorted(os.listdir(OUT)))
