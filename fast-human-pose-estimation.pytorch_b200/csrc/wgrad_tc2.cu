@@ -120,10 +120,10 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < nkt; ++i) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < nkt; ++i, s = (s + 1 == p.stages ? 0 : s + 1), ph ^= (s == 0)) {
         const int kt = kt0 + i;
-        const int s = i % p.stages;
-        const uint32_t ph = (i / p.stages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         const int tw = kt % p.tiles_w, th = (kt / p.tiles_w) % p.tiles_h, tn = kt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
@@ -150,9 +150,9 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(128, (uint32_t)p.N, 1, 1);  // both operands MN-major
-      for (int i = 0; i < nkt; ++i) {
-        const int s = i % p.stages;
-        const uint32_t ph = (i / p.stages) & 1;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < nkt; ++i, s = (s + 1 == p.stages ? 0 : s + 1), ph ^= (s == 0)) {
         mbar_wait(&ready_bar[s], ph);   // transform done (implies the TMA bytes have landed)
         tc_fence_after_sync();
         const uint32_t m_hi = smem_u32(smem + (size_t)s * p.stage_bytes);
@@ -213,10 +213,10 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     const int dn = r / (p.bw * p.bh), dh_ = (r / p.bw) % p.bh, dw_ = r % p.bw;
     const bool has_affine = p.pre_scale != nullptr;
     const uint32_t row_off = (uint32_t)r * 128u + (uint32_t)pc * 16u;
-    for (int i = 0; i < nkt; ++i) {
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < nkt; ++i, s = (s + 1 == p.stages ? 0 : s + 1), ph ^= (s == 0)) {
       const int kt = kt0 + i;
-      const int s = i % p.stages;
-      const uint32_t ph = (i / p.stages) & 1;
       const int tw = kt % p.tiles_w, th = (kt / p.tiles_w) % p.tiles_h, tn = kt / (p.tiles_w * p.tiles_h);
       const int pn = tn * p.bn + dn, hh0 = th * p.bh + dh_, ww0 = tw * p.bw + dw_;
       mbar_wait(&full_bar[s], ph);
@@ -239,9 +239,9 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
           const bool inb = pn < p.B && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W && c < p.Cin;
           if (inb) {
             if (has_affine) {
-              const float4 mu = *reinterpret_cast<const float4*>(s_mean + c);
-              const float4 sc = *reinterpret_cast<const float4*>(s_scale + c);
-              const float4 sh = *reinterpret_cast<const float4*>(s_shift + c);
+              const float4 mu = lds128(smem_u32(s_mean) + (uint32_t)c * 4u);
+              const float4 sc = lds128(smem_u32(s_scale) + (uint32_t)c * 4u);
+              const float4 sh = lds128(smem_u32(s_shift) + (uint32_t)c * 4u);
               v.x = fmaf(v.x - mu.x, sc.x, sh.x); v.y = fmaf(v.y - mu.y, sc.y, sh.y);
               v.z = fmaf(v.z - mu.z, sc.z, sh.z); v.w = fmaf(v.w - mu.w, sc.w, sh.w);
             }
@@ -253,8 +253,8 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
           }
         }
         float4 h, l;
-        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-        split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+        split_tf32_fast(v.x, h.x, l.x); split_tf32_fast(v.y, h.y, l.y);
+        split_tf32_fast(v.z, h.z, l.z); split_tf32_fast(v.w, h.w, l.w);
         sts128(addr, h);
         if (split) sts128(addr + (uint32_t)half_bytes, l);
       }
