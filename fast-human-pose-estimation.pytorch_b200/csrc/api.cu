@@ -107,6 +107,14 @@ int fpd_conv2d_tc_ts(const float* x, const float* pre_mean, const float* pre_sca
                            out_scale, B, H, W, Cin, Cout, ksize, device_sm_count(), S(stream));
 }
 
+int fpd_conv2d_tc_g(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
+                    int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
+                    const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
+                    int ksize, fpd_stream_t stream) {
+  return conv_tc_g_launch(x, pre_mean, pre_scale, pre_shift, pre_relu, w_hi, w_lo, bias, residual, relu_mask, y,
+                          out_scale, B, H, W, Cin, Cout, ksize, device_sm_count(), S(stream));
+}
+
 int fpd_conv2d_wgrad_tc_supported(int Cin, int Cout, int ksize) {
   return wgrad_tc_supported(Cin, Cout, ksize) ? 1 : 0;
 }

@@ -25,6 +25,12 @@ int conv_tc_ts_launch(const float* x, const float* pre_mean, const float* pre_sc
                       const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
                       int ksize, int num_sms, cudaStream_t stream);
 
+// ---- conv_tc4.cu : fused transform, A operand global -> registers -> TMEM (no shared-memory traffic for A) ----
+int conv_tc_g_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
+                     int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
+                     const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
+                     int ksize, int num_sms, cudaStream_t stream);
+
 // ---- wgrad_tc.cu : tcgen05 weight-gradient GEMM (K = pixels) ----
 bool wgrad_tc_supported(int Cin, int Cout, int ksize);
 size_t wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize, int num_sms);

@@ -135,7 +135,8 @@ def conv2d_tc_fused(x, w_hi, w_lo, ksize, mean=None, scale=None, shift=None, rel
     B, H, W, Cin = x.shape
     Cout = w_hi.shape[1]
     y = out if out is not None else torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
-    fn = N.lib().fpd_conv2d_tc_ts if (impl or CONV_FUSED_IMPL) == "ts" else N.lib().fpd_conv2d_tc_fused
+    which = impl or CONV_FUSED_IMPL
+    fn = {"ts": N.lib().fpd_conv2d_tc_ts, "g": N.lib().fpd_conv2d_tc_g, "ss": N.lib().fpd_conv2d_tc_fused}[which]
     N.check(fn(_p(x), _p(mean), _p(scale), _p(shift), int(relu), _p(w_hi), _p(w_lo), _p(bias), _p(residual),
                _p(relu_mask), _p(y), float(out_scale), B, H, W, Cin, Cout, ksize, _stream()), "conv2d_tc_fused")
     return y

@@ -77,6 +77,13 @@ int fpd_conv2d_tc_ts(const float* x, const float* pre_mean, const float* pre_sca
                      const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
                      int ksize, fpd_stream_t stream);
 
+/* Same contract again; the activation tile goes global -> registers -> tensor memory (no shared-memory traffic for the
+ * A operand at all; shared memory carries only the weight tiles). */
+int fpd_conv2d_tc_g(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
+                    int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
+                    const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
+                    int ksize, fpd_stream_t stream);
+
 /* Tensor-core weight gradient: dw_oihw[Cout,Cin,k,k] = scale * sum_pixels dy (x) a(tap-shifted). */
 int fpd_conv2d_wgrad_tc_supported(int Cin, int Cout, int ksize);
 size_t fpd_conv2d_wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize);

@@ -79,7 +79,7 @@ def test_conv2d_tc_forward(shape, passes):
 
 @pytest.mark.parametrize("shape", CONV_TC_SHAPES)
 @pytest.mark.parametrize("passes", [3, 1])
-@pytest.mark.parametrize("impl", ["ss", "ts"])
+@pytest.mark.parametrize("impl", ["ss", "ts", "g"])
 def test_conv2d_tc_fused_bn_relu(shape, passes, impl):
     """conv(relu(bn_affine(x))) with the operand transform inside the kernel vs torch fp32."""
     B, H, W, Cin, Cout, k = shape

@@ -35,7 +35,7 @@ def main():
     shapes = [(32, 64, 64, 128, 128, 3), (32, 64, 64, 64, 64, 3), (32, 64, 64, 128, 64, 1), (32, 64, 64, 64, 128, 1),
               (32, 64, 64, 256, 128, 1), (32, 64, 64, 128, 256, 1), (32, 64, 64, 128, 128, 1), (32, 32, 32, 128, 128, 3),
               (32, 32, 32, 64, 64, 3), (32, 16, 16, 64, 64, 3), (32, 128, 128, 32, 32, 3)]
-    print("%-28s %10s %10s %10s %10s   GF" % ("B,H,W,Cin,Cout,k", "split", "conv_tc", "ss_fused", "ts_fused"))
+    print("%-28s %10s %10s %10s %10s %10s   GF" % ("B,H,W,Cin,Cout,k", "split", "conv_tc", "ss_fused", "ts_fused", "g_fused"))
     for (B, H, W, Cin, Cout, k) in shapes:
         g = torch.Generator(device="cuda").manual_seed(0)
         x = torch.randn(B, H, W, Cin, device="cuda", generator=g)
@@ -50,9 +50,11 @@ def main():
                                                  impl="ss"), flush)
         t_ts = timed(lambda: ops.conv2d_tc_fused(x, w_hi, w_lo, k, mean=mean, scale=scale, shift=shift, relu=True, out=y,
                                                  impl="ts"), flush)
+        t_g = timed(lambda: ops.conv2d_tc_fused(x, w_hi, w_lo, k, mean=mean, scale=scale, shift=shift, relu=True, out=y,
+                                                impl="g"), flush)
         gf = 2.0 * B * H * W * Cin * Cout * k * k / 1e9
-        print("%-28s %10.1f %10.1f %10.1f %10.1f   %.1f" % (str((B, H, W, Cin, Cout, k)), t_split, t_conv, t_ss, t_ts, gf),
-              flush=True)
+        print("%-28s %10.1f %10.1f %10.1f %10.1f %10.1f   %.1f" % (str((B, H, W, Cin, Cout, k)), t_split, t_conv, t_ss, t_ts,
+                                                                   t_g, gf), flush=True)
 
 
 if __name__ == "__main__":
