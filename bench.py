@@ -185,8 +185,9 @@ def run_reference(args, rank):
 # GPU arm
 # --------------------------------------------------------------------------------------------------
 def time_dominant_kernel(B):
-    """Live CUDA-event timing of the dominant kernel (tcgen05 implicit-GEMM conv) on its heaviest shape:
-    teacher 3x3 128->128 @64x64 (18 launches/step = 38.7 % of the teacher's MACs), 3xTF32."""
+    """Live CUDA-event timing of the dominant kernel (conv_tc_ts_kernel: tcgen05 implicit-GEMM conv with the BN/ReLU/
+    tf32-split operand transform fused in, A operand in TMEM) on its heaviest shape: teacher 3x3 128->128 @64x64
+    (18 launches/step = 38.7 % of the teacher's MACs), 3xTF32."""
     import torch
     from fpd_b200 import ops
     H = W = 64
@@ -194,19 +195,24 @@ def time_dominant_kernel(B):
     g = torch.Generator(device="cuda").manual_seed(0)
     x = torch.randn(B, H, W, Cin, device="cuda", generator=g)
     w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) * 0.03
-    a_hi, a_lo = ops.affine_act_split(x)
     w_hi, w_lo = ops.weight_prep(w)
+    mean = torch.zeros(Cin, device="cuda")
+    scale = torch.ones(Cin, device="cuda")
+    shift = torch.zeros(Cin, device="cuda")
     y = torch.empty(B, H, W, Cout, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def launch():
+        ops.conv2d_tc_fused(x, w_hi, w_lo, 3, mean=mean, scale=scale, shift=shift, relu=True, out=y, impl="ts")
     for _ in range(3):
-        ops.conv2d_tc(a_hi, a_lo, w_hi, w_lo, 3, out=y)
+        launch()
     torch.cuda.synchronize()
     iters, tot = 10, 0.0
     for _ in range(iters):
         flush.zero_()  # L2 flush between timed launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.conv2d_tc(a_hi, a_lo, w_hi, w_lo, 3, out=y)
+        launch()
         e1.record()
         torch.cuda.synchronize()
         tot += e0.elapsed_time(e1)
@@ -304,9 +310,11 @@ def run_b200(args, rank, local_rank, world):
         tf32_peak = peaks["bf16_tflops"] / 2.0  # tf32 dense = half the bf16 rate; burst figure: kernel timed alone
         ach = k_flops / (k_ms * 1e-3) / 1e12
         line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
-                            "frac": ach / tf32_peak, "traffic": None,
-                            "kernel": "conv_tc_kernel 3x3 128->128 @64x64 B=%d (3xTF32: 3 MMA passes per "
-                                      "algorithmic FLOP)" % B,
+                            "frac": ach / tf32_peak,
+                            # dram__bytes_read+write of this kernel/shape from profiles/r1_prof_conv_tc_ts.md
+                            "traffic": 87.47e6 if B == 32 else None,
+                            "kernel": "conv_tc_ts_kernel 3x3 128->128 @64x64 B=%d (3xTF32: 3 MMA passes per "
+                                      "algorithmic FLOP; executed-MMA fraction of peak = 3 x frac)" % B,
                             "kernel_ms": k_ms, "peak_source": peak_src + ", tf32 = bf16/2",
                             "step_frac_of_tf32_peak": value / world * FLOP_PER_IMAGE / 1e12 / (
                                 peaks["bf16_tflops_sustained"] / 2.0)}
