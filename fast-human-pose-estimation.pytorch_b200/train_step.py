@@ -68,6 +68,10 @@ class FPDTrainStep:
         self.static = None
         self.losses = None
         self.launches_per_step = None
+        import os
+        self.overlap_teacher = os.environ.get("FPD_OVERLAP_TEACHER", "1") != "0"
+        self._side = torch.cuda.Stream() if (teacher is not None and self.overlap_teacher) else None
+        self._t_keep = None
         student.train()
         if teacher is not None:
             teacher.eval()
@@ -75,12 +79,25 @@ class FPDTrainStep:
     # ------------------------------------------------------------------ the graph body
     def _body(self, x, target, tw):
         s_eng = self.student.engine()
-        ctx = s_eng.forward(x, True, record_tape=True)
-        outs = [v.data for v in ctx.outs]
         t_last = None
-        if self.teacher is not None:
-            t_ctx = self.teacher.engine().forward(x, False, record_tape=False)
-            t_last = t_ctx.outs[-1].data
+        if self.teacher is not None and self.overlap_teacher:
+            # the frozen teacher's forward is independent of the student's: run it on a second stream so its many
+            # small-grid kernels (low-resolution hourglass levels) fill SMs the student leaves idle. It uses no shared
+            # workspace (eval-mode BN: no statistics passes), so the two streams touch disjoint memory.
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                t_ctx = self.teacher.engine().forward(x, False, record_tape=False)
+                self._t_keep = t_ctx            # keep every teacher tensor alive until the streams have joined
+                t_last = t_ctx.outs[-1].data
+            ctx = s_eng.forward(x, True, record_tape=True)
+            main.wait_stream(self._side)
+        else:
+            ctx = s_eng.forward(x, True, record_tape=True)
+            if self.teacher is not None:
+                t_ctx = self.teacher.engine().forward(x, False, record_tape=False)
+                t_last = t_ctx.outs[-1].data
+        outs = [v.data for v in ctx.outs]
         losses, grads = ops.fpd_loss(outs, target, t_last, tw, self.alpha, losses_out=self.losses)
         pg = s_eng.backward(ctx, grads)
         srcs, dsts = [], []
