@@ -264,11 +264,11 @@ def run_b200(args, rank, local_rank, world):
         return ms.item()
 
     for _ in range(max(args.warmup, 3)):
-        step.step(xd, td, wd)
+        step.step(xd, td, wd, next_x=xd)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_total = timed(lambda: step.step(xd, td, wd), args.steps)
+    ms_total = timed(lambda: step.step(xd, td, wd, next_x=xd), args.steps)
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * B / (ms_step / 1000.0)
@@ -277,7 +277,8 @@ def run_b200(args, rank, local_rank, world):
     loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        losses = step.step(xh, th, wh)
+        # the next batch's images are what crosses PCIe each step (this step's were staged by the previous call)
+        losses = step.step(xh, th, wh, next_x=xh)
         loss_host.copy_(losses, non_blocking=False)
 
     for _ in range(2):
@@ -299,6 +300,8 @@ def run_b200(args, rank, local_rank, world):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B,
                        "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph,
+                       "teacher": "second stream, software-pipelined one batch ahead" if step.pipeline else
+                                  ("second stream" if step.overlap_teacher else "same stream"),
                        "l2": "per-step working set (activations ~ several GB) exceeds the 126 MB L2; no flush needed",
                        "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,

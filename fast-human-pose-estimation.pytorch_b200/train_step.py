@@ -70,6 +70,10 @@ class FPDTrainStep:
         self.launches_per_step = None
         import os
         self.overlap_teacher = os.environ.get("FPD_OVERLAP_TEACHER", "1") != "0"
+        self.pipeline = (teacher is not None and use_graph and self.overlap_teacher
+                         and os.environ.get("FPD_PIPELINE_TEACHER", "1") != "0")
+        self.x_next = self.t_cur = self.t_next = None
+        self._have_next = False
         self._side = torch.cuda.Stream() if (teacher is not None and self.overlap_teacher) else None
         self._t_keep = None
         student.train()
@@ -77,6 +81,37 @@ class FPDTrainStep:
             teacher.eval()
 
     # ------------------------------------------------------------------ the graph body
+    def _body_pipelined(self, x, target, tw, x_next):
+        """Same update, with the frozen teacher software-pipelined one batch ahead: while the student does
+        forward/loss/backward on batch i (using the teacher heat-map computed during step i-1), the second stream runs the
+        teacher forward on batch i+1. The teacher's output does not depend on the student, so the result of every step
+        is unchanged; the teacher's ~20 ms simply move off the critical path."""
+        s_eng = self.student.engine()
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            t_ctx = self.teacher.engine().forward(x_next, False, record_tape=False)
+            self._t_keep = t_ctx
+            self.t_next.copy_(t_ctx.outs[-1].data)
+        ctx = s_eng.forward(x, True, record_tape=True)
+        outs = [v.data for v in ctx.outs]
+        losses, grads = ops.fpd_loss(outs, target, self.t_cur, tw, self.alpha, losses_out=self.losses)
+        pg = s_eng.backward(ctx, grads)
+        self._gather_grads(pg)
+        main.wait_stream(self._side)
+        return losses
+
+    def _gather_grads(self, pg):
+        srcs, dsts = [], []
+        for p, gv in zip(self.flat.params, self.flat.grad_views):
+            g = pg.get(p)
+            if g is None:
+                gv.zero_()
+            else:
+                srcs.append(g.reshape(p.shape))
+                dsts.append(gv)
+        torch._foreach_copy_(dsts, srcs)
+
     def _body(self, x, target, tw):
         s_eng = self.student.engine()
         t_last = None
@@ -100,35 +135,38 @@ class FPDTrainStep:
         outs = [v.data for v in ctx.outs]
         losses, grads = ops.fpd_loss(outs, target, t_last, tw, self.alpha, losses_out=self.losses)
         pg = s_eng.backward(ctx, grads)
-        srcs, dsts = [], []
-        for p, gv in zip(self.flat.params, self.flat.grad_views):
-            g = pg.get(p)
-            if g is None:
-                gv.zero_()
-            else:
-                srcs.append(g.reshape(p.shape))
-                dsts.append(gv)
-        torch._foreach_copy_(dsts, srcs)
+        self._gather_grads(pg)
         return losses
+
+    def _run_body(self):
+        if self.pipeline:
+            return self._body_pipelined(self.static[0], self.static[1], self.static[2], self.x_next)
+        return self._body(*self.static)
 
     def _capture(self, x, target, tw):
         self.static = (torch.empty_like(x), torch.empty_like(target), torch.empty_like(tw))
         for s, v in zip(self.static, (x, target, tw)):
             s.copy_(v)
         self.losses = torch.zeros(3, dtype=torch.float32, device=x.device)
+        if self.pipeline:
+            self.x_next = x.clone()
+            with torch.no_grad():
+                t0 = self.teacher.engine().forward(x, False, record_tape=False).outs[-1].data
+            self.t_cur = t0.clone()
+            self.t_next = t0.clone()
         # eager warm-up (lazy init, workspace growth, running-stat semantics identical to a normal step)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             self._saved_bn = self._snapshot_bn()
-            self._body(*self.static)
+            self._run_body()
             self._restore_bn(self._saved_bn)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         n0 = N.lib().fpd_launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self._body(*self.static)
+            self._run_body()
         self.launches_per_step = int(N.lib().fpd_launch_count() - n0) + 1  # + the Adam launch
         self._restore_bn(self._saved_bn)  # capture does not execute, but keep host-side state tidy
 
@@ -140,16 +178,36 @@ class FPDTrainStep:
             b.copy_(s)
 
     # ------------------------------------------------------------------ public
-    def step(self, x, target, target_weight):
+    def step(self, x, target, target_weight, next_x=None):
         """x [B,3,H,W], target [B,J,h,w], target_weight [B,J,1] -- CUDA or pinned-host tensors.
-        Returns the device tensor losses[3] = (pose, kd, total); no host synchronisation."""
+        Returns the device tensor losses[3] = (pose, kd, total); no host synchronisation.
+        With teacher pipelining (`pipeline=True`) pass `next_x`, the NEXT step's images (what a prefetching loader has at
+        hand anyway): the teacher runs on them while the student trains on `x`, and the following call must pass that
+        same batch as `x`. Without `next_x` the teacher for the following step is run up front (no overlap)."""
         tw = target_weight.reshape(target_weight.shape[0], -1)
         if self.use_graph:
             if self.graph is None:
                 xd, td, wd = (t.cuda(non_blocking=True).float().contiguous() for t in (x, target, tw))
                 self._capture(xd, td, wd)
-            for s, v in zip(self.static, (x, target, tw)):
-                s.copy_(v, non_blocking=True)
+                self._have_next = False
+            if self.pipeline:
+                if self._have_next:
+                    # this step's images and teacher heat-map were staged by the previous call
+                    self.static[0].copy_(self.x_next, non_blocking=True)
+                    self.t_cur.copy_(self.t_next, non_blocking=True)
+                else:
+                    self.static[0].copy_(x, non_blocking=True)
+                    with torch.no_grad():
+                        self.t_cur.copy_(self.teacher.engine().forward(self.static[0], False,
+                                                                        record_tape=False).outs[-1].data)
+                self.static[1].copy_(target, non_blocking=True)
+                self.static[2].copy_(tw, non_blocking=True)
+                if next_x is not None:
+                    self.x_next.copy_(next_x, non_blocking=True)
+                self._have_next = next_x is not None
+            else:
+                for s, v in zip(self.static, (x, target, tw)):
+                    s.copy_(v, non_blocking=True)
             self.graph.replay()
             losses = self.losses
         else:

@@ -201,3 +201,76 @@ def test_eval_mode_and_precision_modes():
         finally:
             del os.environ["FPD_PRECISION"]
         assert _rel(got1, ref) < 2e-2   # single-pass TF32: documented as outside the parity bar
+
+
+def test_flip_test_inference_pipeline_matches_oracle():
+    """BASELINE configs[4] path (function.validate, function.py:212-240 + inference.get_max_preds): forward, forward on the
+    W-flipped input, flip_back + 1-px shift + average, arg-max -- all on the device -- against the oracle restatement."""
+    from fpd_b200 import ops
+    from oracle import decode_oracle as D
+    from oracle import hourglass_oracle as O
+    torch.manual_seed(3)
+    net = _net(128, 4)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+    net.eval()
+    B = 4
+    x = torch.randn(B, 3, 256, 256, device="cuda")
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        ref = O.hourglass_net(sd, x, 4, training=False)[-1].cpu().numpy()
+        ref_f = O.hourglass_net(sd, x.flip(3), 4, training=False)[-1].cpu().numpy()
+        hm = net.forward_nhwc(x, training=False)[-1]
+        hm_f = net.forward_nhwc(x.flip(3).contiguous(), training=False)[-1]
+    perm = list(range(16))
+    for a, b in D.MPII_FLIP_PAIRS:
+        perm[a], perm[b] = b, a
+    avg, idx, maxval = ops.flip_merge_argmax(hm, hm_f, torch.tensor(perm, dtype=torch.int32, device="cuda"), shift=True)
+    merged_ref = D.flip_test_merge(ref, ref_f, D.MPII_FLIP_PAIRS, True)
+    preds_ref, max_ref = D.get_max_preds(merged_ref)
+    got = ops.nhwc_to_nchw(avg).cpu().numpy()
+    assert np.abs(got - merged_ref).max() <= TOL * np.abs(merged_ref).max()
+    # arg-max of OUR merged map is bit-exact w.r.t. numpy on the same map ...
+    idx_np = got.reshape(B, 16, -1).argmax(2)
+    assert np.array_equal(idx.cpu().numpy(), idx_np)
+    # ... and agrees with the oracle's key points wherever the top-2 margin exceeds the parity tolerance
+    flat = merged_ref.reshape(B, 16, -1)
+    top2 = np.sort(flat, axis=2)[:, :, -2:]
+    clear = (top2[:, :, 1] - top2[:, :, 0]) > 2 * TOL * np.abs(merged_ref).max()
+    ref_idx = flat.argmax(2)
+    assert np.array_equal(idx.cpu().numpy()[clear], ref_idx[clear])
+    assert clear.mean() > 0.5
+    assert np.abs(maxval.cpu().numpy() - max_ref[..., 0]).max() <= TOL * np.abs(max_ref).max()
+
+
+def test_graph_pipelined_train_step_equals_eager_steps():
+    """FPDTrainStep as a CUDA graph with the teacher on a second stream, software-pipelined one batch ahead, must produce
+    the same losses and weights as plain eager steps (teacher and student on one stream, no graph)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import synthetic_batch
+    from fpd_b200.train_step import FPDTrainStep
+    torch.manual_seed(11)
+    init_s = {k: v.clone() for k, v in _net(64, 2).state_dict().items()}
+    init_t = {k: v.clone() for k, v in _net(64, 1).state_dict().items()}
+    batches = [tuple(t.cuda() for t in synthetic_batch(2, 50 + i, 128, 128)) for i in range(3)]
+
+    def run(use_graph):
+        s, t = _net(64, 2, init_s), _net(64, 1, init_t)
+        st = FPDTrainStep(s, t, alpha=0.5, lr=1e-3, use_graph=use_graph)
+        assert st.pipeline == use_graph
+        losses = []
+        for i, (x, tg, tw) in enumerate(batches):
+            nxt = batches[i + 1][0] if (use_graph and i + 1 < len(batches)) else None
+            losses.append(st.step(x, tg, tw, next_x=nxt).clone())
+        torch.cuda.synchronize()
+        return torch.stack(losses).cpu(), st.flat.flat.clone().cpu(), {k: v.clone().cpu() for k, v in s.state_dict().items()}
+
+    l_e, w_e, sd_e = run(False)
+    l_g, w_g, sd_g = run(True)
+    assert torch.allclose(l_e, l_g, rtol=1e-5, atol=0), (l_e, l_g)
+    assert _rel(w_g, w_e) < 1e-5
+    assert _rel(sd_g["bn1.running_var"], sd_e["bn1.running_var"]) < 1e-6
+    assert int(sd_g["bn1.num_batches_tracked"]) == int(sd_e["bn1.num_batches_tracked"]) == 3
