@@ -71,7 +71,7 @@ class FPDTrainStep:
         import os
         self.overlap_teacher = os.environ.get("FPD_OVERLAP_TEACHER", "1") != "0"
         self.pipeline = (teacher is not None and use_graph and self.overlap_teacher
-                         and os.environ.get("FPD_PIPELINE_TEACHER", "1") != "0")
+                         and os.environ.get("FPD_PIPELINE_TEACHER", "0") != "0")   # measured: no gain over the plain 2nd stream
         self.x_next = self.t_cur = self.t_next = None
         self._have_next = False
         self._side = torch.cuda.Stream() if (teacher is not None and self.overlap_teacher) else None

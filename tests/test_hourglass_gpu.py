@@ -257,6 +257,8 @@ def test_graph_pipelined_train_step_equals_eager_steps():
     init_t = {k: v.clone() for k, v in _net(64, 1).state_dict().items()}
     batches = [tuple(t.cuda() for t in synthetic_batch(2, 50 + i, 128, 128)) for i in range(3)]
 
+    os.environ["FPD_PIPELINE_TEACHER"] = "1"
+
     def run(use_graph):
         s, t = _net(64, 2, init_s), _net(64, 1, init_t)
         st = FPDTrainStep(s, t, alpha=0.5, lr=1e-3, use_graph=use_graph)
@@ -268,8 +270,11 @@ def test_graph_pipelined_train_step_equals_eager_steps():
         torch.cuda.synchronize()
         return torch.stack(losses).cpu(), st.flat.flat.clone().cpu(), {k: v.clone().cpu() for k, v in s.state_dict().items()}
 
-    l_e, w_e, sd_e = run(False)
-    l_g, w_g, sd_g = run(True)
+    try:
+        l_e, w_e, sd_e = run(False)
+        l_g, w_g, sd_g = run(True)
+    finally:
+        del os.environ["FPD_PIPELINE_TEACHER"]
     assert torch.allclose(l_e, l_g, rtol=1e-5, atol=0), (l_e, l_g)
     assert _rel(w_g, w_e) < 1e-5
     assert _rel(sd_g["bn1.running_var"], sd_e["bn1.running_var"]) < 1e-6
