@@ -116,3 +116,40 @@ def test_hrnet_forward_matches_oracle_at_baseline_widths(kind, B, training):
         got = net(x)
     assert tuple(got.shape) == (B, 17, 64, 48)
     assert _rel(got, ref) < TOL, "rel %.3e" % _rel(got, ref)
+
+
+def test_hrnet_fpd_train_step_matches_oracle_losses():
+    """BASELINE configs[3] path at test size: HRNet student (train) + frozen HRNet teacher (eval), FPD loss, backward,
+    flat Adam through FPDTrainStep; loss terms against the oracle (hrnet_oracle + fpd_loss)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from fpd_b200.train_step import FPDTrainStep
+    from oracle import hourglass_oracle as O
+    from oracle import hrnet_oracle as HO
+    torch.manual_seed(21)
+    student = _net("small")
+    teacher = _net("small")
+    for m in teacher.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+    B = 2
+    x = torch.randn(B, 3, 128, 96, device="cuda")
+    target = torch.rand(B, 17, 32, 24, device="cuda")
+    tw = (torch.rand(B, 17, 1, device="cuda") > 0.2).float()
+    s_sd = HO.annotate_strides({k: v.clone() for k, v in student.state_dict().items()})
+    t_sd = HO.annotate_strides({k: v.clone() for k, v in teacher.state_dict().items()})
+    with torch.no_grad():
+        out = HO.hrnet(s_sd, x, training=True)
+        tout = HO.hrnet(t_sd, x, training=False)
+        ref_total, ref_pose, ref_kd = O.fpd_loss([out], target, tw, tout, 0.5)
+    step = FPDTrainStep(student, teacher, alpha=0.5, lr=1e-3, use_graph=False)
+    w0 = step.flat.flat.clone()
+    losses = step.step(x, target, tw)
+    torch.cuda.synchronize()
+    pose, kd, total = [float(v) for v in losses.cpu()]
+    assert abs(pose - ref_pose.item()) < TOL * abs(ref_pose.item())
+    assert abs(kd - ref_kd.item()) < TOL * abs(ref_kd.item())
+    assert abs(total - ref_total.item()) < TOL * abs(ref_total.item())
+    assert not torch.equal(w0, step.flat.flat)
+    assert torch.isfinite(step.flat.flat).all()
