@@ -202,12 +202,33 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       float* yrow = p.y + pix * p.Cout;
       const float* rrow = p.residual ? p.residual + pix * p.Cout : nullptr;
       const float* mrow = p.relu_mask ? p.relu_mask + pix * p.Cout : nullptr;
+      // The residual row does not depend on the MMAs: pull it towards the SM while the accumulator is still being
+      // produced (L2 prefetch of the whole row now, register prefetch one 16-column chunk ahead below); otherwise every
+      // chunk would expose a full global-memory round trip and the epilogue, not the tensor core, sets the tile time.
+      if (rrow && valid) {
+        for (int c = 0; c < p.Cout; c += 32)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + c));
+      }
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + as * (uint32_t)p.tmem_cols + ((uint32_t)(q * 32) << 16);
+      float4 rnext[4];
+      if (rrow && valid) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rnext[j] = __ldg(reinterpret_cast<const float4*>(rrow) + j);
+      }
       for (int c0 = 0; c0 < p.Cout; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
+        float4 rcur[4];
+        if (rrow && valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+          if (c0 + 16 < p.Cout) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rnext[j] = __ldg(reinterpret_cast<const float4*>(rrow + c0 + 16) + j);
+          }
+        }
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
@@ -222,7 +243,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
             }
             if (rrow) {
-              const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + c0 + j));
+              const float4 r = rcur[j >> 2];
               o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
             }
             if (mrow) {

@@ -101,9 +101,12 @@ class HourglassNet(nn.Module):
         return self._engine
 
     def forward(self, x):
-        if not x.is_cuda:
-            raise RuntimeError("fpd_b200 HourglassNet runs on a CUDA (sm_100a) device only; got a %s tensor. "
-                               "There is no CPU fallback." % x.device)
+        dev = self.conv1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("fpd_b200 HourglassNet runs on a CUDA (sm_100a) device only; the module is on %s. "
+                               "There is no CPU fallback: call .cuda() first." % dev)
+        if not x.is_cuda:   # host batch from a DataLoader: stage it like nn.DataParallel's scatter would
+            x = x.to(dev, non_blocking=True)
         from fpd_b200 import autograd_bridge
         return autograd_bridge.run(self, x)
 

@@ -52,9 +52,13 @@ def main():
                                                  impl="ts"), flush)
         t_g = timed(lambda: ops.conv2d_tc_fused(x, w_hi, w_lo, k, mean=mean, scale=scale, shift=shift, relu=True, out=y,
                                                 impl="g"), flush)
+        res = torch.randn(B, H, W, Cout, device="cuda", generator=g)
+        bias = torch.randn(Cout, device="cuda", generator=g)
+        t_res = timed(lambda: ops.conv2d_tc_fused(x, w_hi, w_lo, k, mean=mean, scale=scale, shift=shift, relu=True, out=y,
+                                                  bias=bias, residual=res, impl="ts"), flush)
         gf = 2.0 * B * H * W * Cin * Cout * k * k / 1e9
-        print("%-28s %10.1f %10.1f %10.1f %10.1f %10.1f   %.1f" % (str((B, H, W, Cin, Cout, k)), t_split, t_conv, t_ss, t_ts,
-                                                                   t_g, gf), flush=True)
+        print("%-28s %10.1f %10.1f %10.1f %10.1f %10.1f   %.1f   ts+bias+residual %.1f" % (
+            str((B, H, W, Cin, Cout, k)), t_split, t_conv, t_ss, t_ts, t_g, gf, t_res), flush=True)
 
 
 if __name__ == "__main__":
