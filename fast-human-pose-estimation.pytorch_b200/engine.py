@@ -280,7 +280,18 @@ class Engine:
                 if (c.tc_wgrad and not FUSED_WGRAD) or (need_dx and c.tc_dgrad and not FUSED_DGRAD):
                     dy_hi, dy_lo = ops.affine_act_split(dy, split=split)
                 # ---- weight gradient
-                if c.tc_wgrad and FUSED_WGRAD:
+                if c.tc_wgrad and FUSED_WGRAD and ctx.wgrad_stream is not None:
+                    # dW (and the bias gradient) are leaves of the backward graph: compute them on a side stream so they
+                    # fill the SMs that the small-grid kernels of the critical dgrad/BN chain leave idle
+                    main = torch.cuda.current_stream()
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    with torch.cuda.stream(ctx.wgrad_stream):
+                        ctx.wgrad_stream.wait_event(ev)
+                        ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc_fused(x.data, dy, c.k, mean=mean, scale=scale,
+                                                                         shift=shift, relu=relu, passes=ctx.passes)
+                    ctx.keepalive.append(dy)     # dy must outlive the side-stream kernel (released after the join)
+                elif c.tc_wgrad and FUSED_WGRAD:
                     ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc_fused(x.data, dy, c.k, mean=mean, scale=scale, shift=shift,
                                                                      relu=relu, passes=ctx.passes)
                 elif c.tc_wgrad:
@@ -407,14 +418,20 @@ class Engine:
         ctx.outs = outs
         return ctx
 
-    def backward(self, ctx, out_grads_nhwc):
-        """out_grads_nhwc: list (per stack) of NHWC gradient tensors or None. Returns {param: grad}."""
+    def backward(self, ctx, out_grads_nhwc, wgrad_stream=None):
+        """out_grads_nhwc: list (per stack) of NHWC gradient tensors or None. Returns {param: grad}.
+        wgrad_stream: optional second CUDA stream for the weight-gradient kernels (joined before returning)."""
+        ctx.wgrad_stream = wgrad_stream
+        ctx.keepalive = []
         for v, g in zip(ctx.outs, out_grads_nhwc):
             if g is not None:
                 v.add_grad(g, owned=False)
         for fn in reversed(ctx.tape):
             fn()
         ctx.tape = None
+        if wgrad_stream is not None:
+            torch.cuda.current_stream().wait_stream(wgrad_stream)
+        ctx.keepalive = []
         return ctx.pgrads
 
 
@@ -428,3 +445,5 @@ class _Ctx:
         self.pgrads = {}
         self.nbt = []
         self.outs = None
+        self.wgrad_stream = None
+        self.keepalive = []

@@ -28,16 +28,21 @@ def _chk(t, name):
 
 
 class Workspace:
-    """Grow-only scratch buffer handed to the kernels that need one (no allocation at call time once warm)."""
+    """Grow-only scratch buffers handed to the kernels that need one (no allocation at call time once warm).
+    One buffer per CUDA stream: kernels enqueued on different streams (teacher / weight-gradient side streams) may run
+    concurrently and must not share reduction scratch."""
 
     def __init__(self):
-        self.buf = None
+        self.bufs = {}
 
     def get(self, nbytes, device):
         nbytes = int(nbytes)
-        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
-            self.buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        return self.buf
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            self.bufs[key] = buf
+        return buf
 
 
 _ws = Workspace()

@@ -76,6 +76,7 @@ class FPDTrainStep:
         self._have_next = False
         self._side = torch.cuda.Stream() if (teacher is not None and self.overlap_teacher) else None
         self._t_keep = None
+        self._wstream = torch.cuda.Stream() if os.environ.get("FPD_WGRAD_STREAM", "1") != "0" else None
         student.train()
         if teacher is not None:
             teacher.eval()
@@ -96,7 +97,7 @@ class FPDTrainStep:
         ctx = s_eng.forward(x, True, record_tape=True)
         outs = [v.data for v in ctx.outs]
         losses, grads = ops.fpd_loss(outs, target, self.t_cur, tw, self.alpha, losses_out=self.losses)
-        pg = s_eng.backward(ctx, grads)
+        pg = s_eng.backward(ctx, grads, wgrad_stream=self._wstream)
         self._gather_grads(pg)
         main.wait_stream(self._side)
         return losses
@@ -134,7 +135,7 @@ class FPDTrainStep:
                 t_last = t_ctx.outs[-1].data
         outs = [v.data for v in ctx.outs]
         losses, grads = ops.fpd_loss(outs, target, t_last, tw, self.alpha, losses_out=self.losses)
-        pg = s_eng.backward(ctx, grads)
+        pg = s_eng.backward(ctx, grads, wgrad_stream=self._wstream)
         self._gather_grads(pg)
         return losses
 
