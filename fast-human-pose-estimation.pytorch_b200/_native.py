@@ -27,6 +27,7 @@ _SIGNATURES = {
     "fpd_conv2d_tc": (c_int, [P, P, P, P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "fpd_conv2d_tc_fused": (c_int, [P, P, P, P, c_int, P, P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int,
                                     c_int, P]),
+    "fpd_conv2d_tc_ts_supported": (c_int, [c_int, c_int, c_int]),
     "fpd_conv2d_tc_ts": (c_int, [P, P, P, P, c_int, P, P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int,
                                  c_int, P]),
     "fpd_conv2d_tc_g": (c_int, [P, P, P, P, c_int, P, P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int,

@@ -99,6 +99,8 @@ int fpd_conv2d_tc_fused(const float* x, const float* pre_mean, const float* pre_
                               out_scale, B, H, W, Cin, Cout, ksize, device_sm_count(), S(stream));
 }
 
+int fpd_conv2d_tc_ts_supported(int Cin, int Cout, int ksize) { return conv_tc_ts_supported(Cin, Cout, ksize) ? 1 : 0; }
+
 int fpd_conv2d_tc_ts(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                      int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
                      const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,

@@ -47,6 +47,7 @@ struct Conv2Params {
   int bn, bh, bw;
   int tiles_w, tiles_h, tiles_n, num_tiles;
   int stages, b_bytes, tmem_cols, acc_stages, a_col0;
+  int nt, n_tiles;   // output channels are processed in n_tiles slices of nt (<= 256) columns; tile = m_tile * n_tiles + n_tile
   const float* pre_mean;   // [Cin] or null (0)
   const float* pre_scale;  // [Cin] or null (identity affine)
   const float* pre_shift;  // [Cin]
@@ -128,10 +129,12 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int tw = tile % p.tiles_w;
-        const int th = (tile / p.tiles_w) % p.tiles_h;
-        const int tn = tile / (p.tiles_w * p.tiles_h);
+        const int mt = tile / p.n_tiles;
+        const int tw = mt % p.tiles_w;
+        const int th = (mt / p.tiles_w) % p.tiles_h;
+        const int tn = mt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+        const int n0w = (tile % p.n_tiles) * p.nt;   // first output channel of this slice
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dh = (p.taps == 9) ? (tap / 3 - 1) : 0;
           const int dw = (p.taps == 9) ? (tap % 3 - 1) : 0;
@@ -140,8 +143,8 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             uint8_t* st = smem + (size_t)s * stage_bytes;
             mbar_expect_tx(&full_bar[s], tx_bytes);
             tma_load_4d(st, &tm_x, &full_bar[s], cb * kBlockK, w0 + dw, h0 + dh, n0);
-            tma_load_3d(st + kABytes, &tm_w_hi, &full_bar[s], cb * kBlockK, 0, tap);
-            if (split) tma_load_3d(st + kABytes + p.b_bytes, &tm_w_lo, &full_bar[s], cb * kBlockK, 0, tap);
+            tma_load_3d(st + kABytes, &tm_w_hi, &full_bar[s], cb * kBlockK, n0w, tap);
+            if (split) tma_load_3d(st + kABytes + p.b_bytes, &tm_w_lo, &full_bar[s], cb * kBlockK, n0w, tap);
           }
         }
       }
@@ -149,7 +152,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(kTileM, (uint32_t)p.Cout, 0, 0);
+      const uint32_t idesc = umma_idesc_tf32(kTileM, (uint32_t)p.nt, 0, 0);
       uint32_t tile_iter = 0;
       int s = 0;
       uint32_t ph = 0;
@@ -191,22 +194,25 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
       const uint32_t as = p.acc_stages == 2 ? (tile_iter & 1) : 0u;
       const uint32_t aph = (p.acc_stages == 2 ? (tile_iter >> 1) : tile_iter) & 1;
-      const int tw = tile % p.tiles_w;
-      const int th = (tile / p.tiles_w) % p.tiles_h;
-      const int tn = tile / (p.tiles_w * p.tiles_h);
+      const int mt = tile / p.n_tiles;
+        const int tw = mt % p.tiles_w;
+      const int th = (mt / p.tiles_w) % p.tiles_h;
+      const int tn = mt / (p.tiles_w * p.tiles_h);
       const int pw = tw * p.bw + (m % p.bw);
       const int ph_ = th * p.bh + (m / p.bw) % p.bh;
       const int pn = tn * p.bn + m / (p.bw * p.bh);
       const bool valid = pn < p.B;
       const size_t pix = ((size_t)pn * p.H + ph_) * p.W + pw;
-      float* yrow = p.y + pix * p.Cout;
-      const float* rrow = p.residual ? p.residual + pix * p.Cout : nullptr;
-      const float* mrow = p.relu_mask ? p.relu_mask + pix * p.Cout : nullptr;
+      const int nc0 = (tile % p.n_tiles) * p.nt;   // channel slice of this tile
+      float* yrow = p.y + pix * p.Cout + nc0;
+      const float* rrow = p.residual ? p.residual + pix * p.Cout + nc0 : nullptr;
+      const float* mrow = p.relu_mask ? p.relu_mask + pix * p.Cout + nc0 : nullptr;
+      const float* brow = p.bias ? p.bias + nc0 : nullptr;
       // The residual row does not depend on the MMAs: pull it towards the SM while the accumulator is still being
       // produced (L2 prefetch of the whole row now, register prefetch one 16-column chunk ahead below); otherwise every
       // chunk would expose a full global-memory round trip and the epilogue, not the tensor core, sets the tile time.
       if (rrow && valid) {
-        for (int c = 0; c < p.Cout; c += 32)
+        for (int c = 0; c < p.nt; c += 32)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + c));
       }
       mbar_wait(&tmem_full[as], aph);
@@ -217,14 +223,14 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 4; ++j) rnext[j] = __ldg(reinterpret_cast<const float4*>(rrow) + j);
       }
-      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+      for (int c0 = 0; c0 < p.nt; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         float4 rcur[4];
         if (rrow && valid) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-          if (c0 + 16 < p.Cout) {
+          if (c0 + 16 < p.nt) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) rnext[j] = __ldg(reinterpret_cast<const float4*>(rrow + c0 + 16) + j);
           }
@@ -238,8 +244,8 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             o.y = __uint_as_float(v[j + 1]) * p.out_scale;
             o.z = __uint_as_float(v[j + 2]) * p.out_scale;
             o.w = __uint_as_float(v[j + 3]) * p.out_scale;
-            if (p.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+            if (brow) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(brow + c0 + j));
               o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
             }
             if (rrow) {
@@ -276,9 +282,10 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint32_t ph = 0;
     const uint32_t s_mean_a = smem_u32(s_mean), s_scale_a = smem_u32(s_scale), s_shift_a = smem_u32(s_shift);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int tw = tile % p.tiles_w;
-      const int th = (tile / p.tiles_w) % p.tiles_h;
-      const int tn = tile / (p.tiles_w * p.tiles_h);
+      const int mt = tile / p.n_tiles;
+        const int tw = mt % p.tiles_w;
+      const int th = (mt / p.tiles_w) % p.tiles_h;
+      const int tn = mt / (p.tiles_w * p.tiles_h);
       const int pn = tn * p.bn + dn;
       const int h_base = th * p.bh + dh_, w_base = tw * p.bw + dw_;
       for (int tap = 0; tap < p.taps; ++tap) {
@@ -342,11 +349,26 @@ int pow2_floor_div(int x, int cap) {
 
 }  // namespace
 
+// Output channels are processed in slices of nt columns: the widest divisor of Cout that is a multiple of 16 and at
+// most 128, so that two accumulator stages (2 x 128 columns) and four A stages (4 x 64 columns) fit the 512 TMEM
+// columns and the epilogue of one slice overlaps the MMAs of the next (Cout = 256 -> 2 x 128, 384 -> 3 x 128, 192 -> 2 x 96).
+int conv_tc_ts_slice(int Cout) {
+  if (Cout <= 128) return Cout;
+  for (int nt = 128; nt >= 16; nt -= 16)
+    if (Cout % nt == 0) return nt;
+  return 0;
+}
+
+bool conv_tc_ts_supported(int Cin, int Cout, int ksize) {
+  return (ksize == 1 || ksize == 3) && Cin % 4 == 0 && Cin >= 4 && Cin <= kMaxCin && Cout % 16 == 0 && Cout >= 16 &&
+         Cout <= 1024 && conv_tc_ts_slice(Cout) > 0;
+}
+
 int conv_tc_ts_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                          int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
                          const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
                          int ksize, int num_sms, cudaStream_t stream) {
-  FPD_REQUIRE(conv_tc_supported(Cin, Cout, ksize), "conv_tc_ts: unsupported shape Cin=%d Cout=%d k=%d", Cin, Cout,
+  FPD_REQUIRE(conv_tc_ts_supported(Cin, Cout, ksize), "conv_tc_ts: unsupported shape Cin=%d Cout=%d k=%d", Cin, Cout,
               ksize);
   FPD_REQUIRE(Cin <= kMaxCin, "conv_tc_ts: Cin=%d exceeds %d", Cin, kMaxCin);
   FPD_REQUIRE(x && w_hi && y, "conv_tc_ts: null operand");
@@ -360,10 +382,12 @@ int conv_tc_ts_launch(const float* x, const float* pre_mean, const float* pre_sc
   p.bh = pow2_floor_div(H, kTileM / p.bw);
   p.bn = kTileM / (p.bw * p.bh);
   p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.tiles_n = (B + p.bn - 1) / p.bn;
-  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  p.b_bytes = Cout * 128;
+  p.nt = conv_tc_ts_slice(Cout);
+  p.n_tiles = Cout / p.nt;
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  p.b_bytes = p.nt * 128;
   int tc = 32;
-  while (tc < Cout) tc *= 2;
+  while (tc < p.nt) tc *= 2;
   p.tmem_cols = tc;
   p.pre_mean = pre_mean; p.pre_scale = pre_scale; p.pre_shift = pre_shift; p.pre_relu = pre_relu;
   p.bias = bias; p.residual = residual; p.relu_mask = relu_mask; p.y = y; p.out_scale = out_scale;
@@ -391,7 +415,7 @@ int conv_tc_ts_launch(const float* x, const float* pre_mean, const float* pre_sc
   {
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)p.taps};
     uint64_t strides[2] = {(uint64_t)Cin * 4, (uint64_t)Cout * Cin * 4};
-    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)Cout, 1};
+    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)p.nt, 1};
     int rc = encode_tmap(&tm_w_hi, w_hi, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = encode_tmap(&tm_w_lo, w_lo ? w_lo : w_hi, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);

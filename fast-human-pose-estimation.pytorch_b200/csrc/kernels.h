@@ -20,6 +20,8 @@ int conv_tc_fused_launch(const float* x, const float* pre_mean, const float* pre
                          int ksize, int num_sms, cudaStream_t stream);
 
 // ---- conv_tc3.cu : fused operand transform with the A operand in tensor memory (TS-mode MMA) ----
+bool conv_tc_ts_supported(int Cin, int Cout, int ksize);   // wider than conv_tc_supported: Cout up to 1024 in slices
+int conv_tc_ts_slice(int Cout);
 int conv_tc_ts_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                       int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
                       const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,

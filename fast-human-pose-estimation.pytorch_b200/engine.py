@@ -85,11 +85,13 @@ class ConvRef:
 
     @property
     def tc_fwd(self):
-        return self.stride == 1 and self.pad == self.k // 2 and ops.conv2d_tc_supported(self.cin, self.cout, self.k)
+        return self.stride == 1 and self.pad == self.k // 2 and ops.conv2d_tc_supported(self.cin, self.cout, self.k,
+                                                                                         fused=FUSED_FWD)
 
     @property
     def tc_dgrad(self):
-        return self.stride == 1 and self.pad == self.k // 2 and ops.conv2d_tc_supported(self.cout, self.cin, self.k)
+        return self.stride == 1 and self.pad == self.k // 2 and ops.conv2d_tc_supported(self.cout, self.cin, self.k,
+                                                                                         fused=FUSED_DGRAD)
 
     @property
     def tc_wgrad(self):

@@ -48,7 +48,10 @@ class Workspace:
 _ws = Workspace()
 
 
-def conv2d_tc_supported(cin, cout, k):
+def conv2d_tc_supported(cin, cout, k, fused=False):
+    """fused=True asks about the kernel conv2d_tc_fused dispatches to (the TS kernel takes Cout > 256 in slices)."""
+    if fused and CONV_FUSED_IMPL == "ts":
+        return bool(N.lib().fpd_conv2d_tc_ts_supported(cin, cout, k))
     return bool(N.lib().fpd_conv2d_tc_supported(cin, cout, k))
 
 

@@ -72,6 +72,7 @@ int fpd_conv2d_tc_fused(const float* x, const float* pre_mean, const float* pre_
 
 /* Same contract as fpd_conv2d_tc_fused, but the prepared A tiles are written to tensor memory and the MMAs run in
  * TS mode (A from TMEM, B from shared memory): removes the shared-memory-bandwidth bound of the SS form for Cout <= 128. */
+int fpd_conv2d_tc_ts_supported(int Cin, int Cout, int ksize); /* Cout up to 1024, processed in <=128-column slices */
 int fpd_conv2d_tc_ts(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                      int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
                      const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,

@@ -56,6 +56,8 @@ CONV_TC_SHAPES = [
     (2, 32, 24, 48, 96, 3),    # HRNet-w48 widths
     (2, 16, 12, 96, 48, 1),
 ]
+# shapes only the sliced TS kernel takes (Cout > 256): HRNet-w48's 384-channel branch
+CONV_TS_WIDE_SHAPES = [(2, 8, 6, 384, 384, 3), (2, 8, 6, 192, 384, 1), (1, 16, 16, 64, 512, 1)]
 
 
 @pytest.mark.parametrize("shape", CONV_TC_SHAPES)
@@ -104,6 +106,23 @@ def test_conv2d_tc_fused_bn_relu(shape, passes, impl):
     tol = 2e-5 if passes == 3 else 3e-3
     assert relerr(nchw(y), ref) < tol, "fused %s passes=%d rel err %.3e" % (shape, passes, relerr(nchw(y), ref))
     assert relerr(nchw(y2), ref2) < tol
+
+
+@pytest.mark.parametrize("shape", CONV_TS_WIDE_SHAPES)
+def test_conv2d_tc_ts_wide_output_slices(shape):
+    B, H, W, Cin, Cout, k = shape
+    o = ops()
+    assert o.N.lib().fpd_conv2d_tc_ts_supported(Cin, Cout, k) == 1 and not o.N.lib().fpd_conv2d_tc_supported(Cin, Cout, k)
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * (1.0 / (Cin * k * k) ** 0.5)
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(B, Cout, H, W, device="cuda", generator=g)
+    ref = F.conv2d(F.relu(x), w, bias, padding=k // 2) + res
+    w_hi, w_lo = o.weight_prep(w)
+    y = o.conv2d_tc_fused(nhwc(x), w_hi, w_lo, k, relu=True, bias=bias, residual=nhwc(res), impl="ts")
+    torch.cuda.synchronize()
+    assert relerr(nchw(y), ref) < 2e-5
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 64, 64, 64, 3), (2, 32, 32, 128, 64, 1), (4, 8, 8, 64, 128, 1)])
