@@ -28,6 +28,8 @@
 //
 // Warp roles (448 threads, persistent): warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2-5 epilogue,
 // warps 6-13 transform.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -47,6 +49,7 @@ struct Conv2Params {
   int bn, bh, bw;
   int tiles_w, tiles_h, tiles_n, num_tiles;
   int stages, b_bytes, tmem_cols, acc_stages, a_col0;
+  int epi_prefetch;  // prefetch the residual row (L2 + one chunk ahead in registers) in the epilogue
   int nt, n_tiles;   // output channels are processed in n_tiles slices of nt (<= 256) columns; tile = m_tile * n_tiles + n_tile
   const float* pre_mean;   // [Cin] or null (0)
   const float* pre_scale;  // [Cin] or null (identity affine)
@@ -211,7 +214,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       // The residual row does not depend on the MMAs: pull it towards the SM while the accumulator is still being
       // produced (L2 prefetch of the whole row now, register prefetch one 16-column chunk ahead below); otherwise every
       // chunk would expose a full global-memory round trip and the epilogue, not the tensor core, sets the tile time.
-      if (rrow && valid) {
+      if (rrow && valid && p.epi_prefetch) {
         for (int c = 0; c < p.nt; c += 32)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + c));
       }
@@ -219,7 +222,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + as * (uint32_t)p.tmem_cols + ((uint32_t)(q * 32) << 16);
       float4 rnext[4];
-      if (rrow && valid) {
+      if (rrow && valid && p.epi_prefetch) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) rnext[j] = __ldg(reinterpret_cast<const float4*>(rrow) + j);
       }
@@ -228,11 +231,16 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         tmem_ld16(taddr + c0, v);
         float4 rcur[4];
         if (rrow && valid) {
+          if (p.epi_prefetch) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-          if (c0 + 16 < p.nt) {
+            for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+            if (c0 + 16 < p.nt) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) rnext[j] = __ldg(reinterpret_cast<const float4*>(rrow + c0 + 16) + j);
+              for (int j = 0; j < 4; ++j) rnext[j] = __ldg(reinterpret_cast<const float4*>(rrow + c0 + 16) + j);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rcur[j] = __ldg(reinterpret_cast<const float4*>(rrow + c0) + j);
           }
         }
         tmem_ld_wait();
@@ -382,6 +390,10 @@ int conv_tc_ts_launch(const float* x, const float* pre_mean, const float* pre_sc
   p.bh = pow2_floor_div(H, kTileM / p.bw);
   p.bn = kTileM / (p.bw * p.bh);
   p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.tiles_n = (B + p.bn - 1) / p.bn;
+  {
+    static const int pf = [] { const char* e = getenv("FPD_EPI_PREFETCH"); return (e && e[0] == '0') ? 0 : 1; }();
+    p.epi_prefetch = pf;
+  }
   p.nt = conv_tc_ts_slice(Cout);
   p.n_tiles = Cout / p.nt;
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;

@@ -12,7 +12,7 @@ namespace fpd {
 namespace {
 
 constexpr int kRedThreads = 256;
-constexpr int kMaxRedBlocks = 1184;  // 8 x 148 SMs
+constexpr int kMaxRedBlocks = 592;   // 4 x 148 SMs: enough bytes in flight for HBM, and a short second stage
 
 struct RedGeom {
   int L;       // float4 lanes across channels (C/4)

@@ -76,7 +76,7 @@ class FPDTrainStep:
         self._have_next = False
         self._side = torch.cuda.Stream() if (teacher is not None and self.overlap_teacher) else None
         self._t_keep = None
-        self._wstream = torch.cuda.Stream() if os.environ.get("FPD_WGRAD_STREAM", "1") != "0" else None
+        self._wstream = torch.cuda.Stream() if os.environ.get("FPD_WGRAD_STREAM", "0") != "0"   # measured: no gain (big kernels cannot co-reside) else None
         student.train()
         if teacher is not None:
             teacher.eval()
