@@ -391,7 +391,7 @@ int conv_tc_ts_launch(const float* x, const float* pre_mean, const float* pre_sc
   p.bn = kTileM / (p.bw * p.bh);
   p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.tiles_n = (B + p.bn - 1) / p.bn;
   {
-    static const int pf = [] { const char* e = getenv("FPD_EPI_PREFETCH"); return (e && e[0] == '0') ? 0 : 1; }();
+    static const int pf = [] { const char* e = getenv("FPD_EPI_PREFETCH"); return (e && e[0] == '1') ? 1 : 0; }();   // measured slightly slower (tools/bench_conv_variants.py): off
     p.epi_prefetch = pf;
   }
   p.nt = conv_tc_ts_slice(Cout);

@@ -76,7 +76,8 @@ class FPDTrainStep:
         self._have_next = False
         self._side = torch.cuda.Stream() if (teacher is not None and self.overlap_teacher) else None
         self._t_keep = None
-        self._wstream = torch.cuda.Stream() if os.environ.get("FPD_WGRAD_STREAM", "0") != "0"   # measured: no gain (big kernels cannot co-reside) else None
+        # weight gradients on a third stream: measured no gain (the big kernels cannot co-reside on an SM), off by default
+        self._wstream = torch.cuda.Stream() if os.environ.get("FPD_WGRAD_STREAM", "0") != "0" else None
         student.train()
         if teacher is not None:
             teacher.eval()

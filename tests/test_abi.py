@@ -36,3 +36,18 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     import pytest
     with pytest.raises(N.NativeLibraryMissing):
         N.lib()
+
+
+def test_every_host_module_imports_on_cpu():
+    """Import (= byte-compile) every Python module of the package and the top-level scripts: no GPU needed."""
+    import importlib
+    import fpd_b200  # noqa: F401
+    for name in ("_native", "ops", "engine", "engine_hrnet", "autograd_bridge", "train_step", "parallel",
+                 "lib.models.hourglass", "lib.models.pose_hrnet", "lib.core.loss", "lib.core.function",
+                 "lib.core.inference", "lib.core.evaluate", "lib.utils.transforms", "lib.nms.nms"):
+        importlib.import_module("fpd_b200." + name)
+    import ast
+    for script in ("bench.py", "__graft_entry__.py", "tools/profile_step.py", "tools/profile_kernel.py",
+                   "tools/profile_convs.py", "tools/bench_conv_variants.py", "tools/diag_net.py", "tools/diag_grad.py",
+                   "tools/summarize_profiles.py"):
+        ast.parse(open(os.path.join(ROOT, script)).read(), script)

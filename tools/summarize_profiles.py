@@ -76,4 +76,8 @@ if __name__ == "__main__":
     launches(tag)
     report(tag, "prof_conv_tc_ss", "conv_tc_kernel (SS, pre-split operands), 3x3 128->128 @64x64, B=32, 3xTF32")
     report(tag, "prof_conv_tc_ts", "conv_tc_ts_kernel (fused transform, A in TMEM), 3x3 128->128 @64x64, B=32, 3xTF32")
+    report(tag, "prof_wgrad_tc_fused", "wgrad_tc_fused_kernel, 3x3 64->64 @64x64, B=32, 3xTF32")
+    cup = os.path.join(SRC, "step_cupti_%s.txt" % tag)
+    if os.path.exists(cup):
+        shutil.copy(cup, os.path.join(OUT, "%s_step_cupti.txt" % tag))
     print(sorted(os.listdir(OUT)))
