@@ -43,6 +43,11 @@ static EncodeTiledFn get_encode_fn() {
 
 int encode_tmap(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                 const uint32_t* box, CUtensorMapSwizzle swz) {
+  return encode_tmap_dt(out, gptr, 0, rank, dims, strides_bytes, box, swz);
+}
+
+int encode_tmap_dt(CUtensorMap* out, const void* gptr, int dtype, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled not available from the driver");
@@ -57,7 +62,7 @@ int encode_tmap(CUtensorMap* out, const void* gptr, int rank, const uint64_t* di
     es[i] = 1;
   }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(gptr), d, s, b, es,
+  CUresult r = fn(out, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(gptr), d, s, b, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -115,6 +120,28 @@ int fpd_conv2d_tc_g(const float* x, const float* pre_mean, const float* pre_scal
                     int ksize, fpd_stream_t stream) {
   return conv_tc_g_launch(x, pre_mean, pre_scale, pre_shift, pre_relu, w_hi, w_lo, bias, residual, relu_mask, y,
                           out_scale, B, H, W, Cin, Cout, ksize, device_sm_count(), S(stream));
+}
+
+int fpd_conv2d_tc_h_supported(int Cin, int Cout, int ksize, int H, int W, int f16) {
+  return conv_tc_h_supported(Cin, Cout, ksize, H, W, f16) ? 1 : 0;
+}
+
+int fpd_conv2d_tc_h(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
+                    int pre_relu, const void* w_hi, const void* w_lo, int f16, const float* bias,
+                    const float* residual, const float* relu_mask, float* y, float out_scale, int B, int H, int W,
+                    int Cin, int Cout, int ksize, fpd_stream_t stream) {
+  return conv_tc_h_launch(x, pre_mean, pre_scale, pre_shift, pre_relu, w_hi, w_lo, f16, bias, residual, relu_mask, y,
+                          out_scale, B, H, W, Cin, Cout, ksize, device_sm_count(), S(stream));
+}
+
+int fpd_conv2d_tc_h_set_profile_buffer(long long* device_buf) {
+  conv_tc_h_set_profile_buffer(device_buf);
+  return FPD_OK;
+}
+
+int fpd_weight_prep_f16(const float* w, void* w_hi, void* w_lo, int O, int I, int k, int for_dgrad,
+                        fpd_stream_t stream) {
+  return weight_prep_f16(w, w_hi, w_lo, O, I, k, for_dgrad, S(stream));
 }
 
 int fpd_conv2d_wgrad_tc_supported(int Cin, int Cout, int ksize) {

@@ -281,5 +281,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t M, uint32_t N, u
 // ------------------------------------------------------------------------------------------------
 int encode_tmap(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                 const uint32_t* box, CUtensorMapSwizzle swz);
+// dtype: 0 = fp32 elements, 1 = fp16 elements (dims / box in elements, strides in bytes)
+int encode_tmap_dt(CUtensorMap* out, const void* gptr, int dtype, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
 
 }  // namespace fpd

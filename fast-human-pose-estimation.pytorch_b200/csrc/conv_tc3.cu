@@ -100,7 +100,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     if (split) tma_prefetch_desc(&tm_w_lo);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&ready_bar[s], kTransformThreads);
+      mbar_init(&ready_bar[s], kTransformThreads / 32);
       mbar_init(&empty_bar[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -335,7 +335,8 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           if (split) tmem_st16(ta + 32u, lo);
           tmem_st_wait();
           tc_fence_before_sync();
-          mbar_arrive(&ready_bar[s]);
+          __syncwarp();                   // one arrival per warp: 256 per-thread arrivals on one barrier serialise
+          if (lane == 0) mbar_arrive(&ready_bar[s]);
         }
       }
     }

@@ -4,6 +4,8 @@
 // (hourglass.py:82,124), nearest-2x upsample + add (hourglass.py:60,90-91), layout converts, weight
 // re-layout. All kernels are vectorised (float4 along the channel axis = the contiguous NHWC axis) and
 // sized for >= 2 waves of 148 SMs; reductions are deterministic (fixed-order partial buffers, no atomics).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -512,6 +514,30 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, float* __restric
   }
 }
 
+// fp16 hi/lo operand form of the weights for the 3xFP16 convolution (conv_tc5.cu): w * 2^scale_log2 = hi + lo with
+// hi = fp16(w'), lo = fp16(w' - hi); the power-of-two pre-scale keeps lo out of the fp16 subnormal range for ordinary
+// weight magnitudes (|w| ~ 1e-2) and is undone exactly in the convolution epilogue. Saturates at +-65504.
+__global__ void weight_prep_f16_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo,
+                                       int O, int I, int k, int for_dgrad, float scale) {
+  const int taps = k * k;
+  const int64_t n = (int64_t)O * I * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    int col, row, tap;
+    float v;
+    if (!for_dgrad) {  // [tap][O][I]
+      col = (int)(t % I); t /= I; row = (int)(t % O); tap = (int)(t / O);
+      v = w[((size_t)row * I + col) * taps + tap];
+    } else {           // [tap'][I][O] with tap' = taps-1-tap (180-degree flip)
+      col = (int)(t % O); t /= O; row = (int)(t % I); tap = (int)(t / I);
+      v = w[((size_t)col * I + row) * taps + (taps - 1 - tap)];
+    }
+    v = fminf(fmaxf(v * scale, -65504.f), 65504.f);
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2half_rn(v - __half2float(h));
+  }
+}
 
 // ---- HRNet glue (reference lib/models/pose_hrnet.py:256-263 fuse, :41-57 BasicBlock tail) -------------------
 struct FuseTerms {
@@ -814,6 +840,15 @@ int weight_prep(const float* w_oihw, float* w_hi, float* w_lo, int O, int I, int
                 cudaStream_t stream) {
   const int64_t n = (int64_t)O * I * k * k;
   weight_prep_kernel<<<grid_for(n, 256), 256, 0, stream>>>(w_oihw, w_hi, w_lo, O, I, k, for_dgrad);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int weight_prep_f16(const float* w_oihw, void* w_hi, void* w_lo, int O, int I, int k, int for_dgrad,
+                    cudaStream_t stream) {
+  const int64_t n = (int64_t)O * I * k * k;
+  weight_prep_f16_kernel<<<grid_for(n, 256), 256, 0, stream>>>(w_oihw, (__half*)w_hi, (__half*)w_lo, O, I, k, for_dgrad,
+                                                               (float)(1 << kF16WeightScaleLog2));
   FPD_LAUNCH_CHECK();
   return FPD_OK;
 }

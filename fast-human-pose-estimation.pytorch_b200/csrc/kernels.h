@@ -33,6 +33,17 @@ int conv_tc_g_launch(const float* x, const float* pre_mean, const float* pre_sca
                      const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
                      int ksize, int num_sms, cudaStream_t stream);
 
+// ---- conv_tc5.cu : halo-tile reuse (3x3: one fetch + one transform per channel block, nine shifted smem->TMEM copies)
+//      and optional 3xFP16 operands (f16 = 1: w_hi / w_lo are __half [tap][Cout][Cin] from weight_prep_f16, pre-scaled
+//      by 2^kF16WeightScaleLog2; f16 = 0: fp32 containers from weight_prep, 3xTF32) ----
+constexpr int kF16WeightScaleLog2 = 8;
+bool conv_tc_h_supported(int Cin, int Cout, int ksize, int H, int W, int f16);
+void conv_tc_h_set_profile_buffer(long long* buf);   // per-CTA stall counters [grid][16] (tools/diag_conv_h.py); null = off
+int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
+                     int pre_relu, const void* w_hi, const void* w_lo, int f16, const float* bias,
+                     const float* residual, const float* relu_mask, float* y, float out_scale, int B, int H, int W,
+                     int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream);
+
 // ---- wgrad_tc.cu : tcgen05 weight-gradient GEMM (K = pixels) ----
 bool wgrad_tc_supported(int Cin, int Cout, int ksize);
 size_t wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize, int num_sms);
@@ -111,6 +122,9 @@ int affine_act_bwd(const float* da, const float* x, const float* mean, const flo
 // OIHW fp32 -> [tap][O][I] (fwd) or [flipped tap][I][O] (dgrad), split into tf32 hi/lo
 int weight_prep(const float* w_oihw, float* w_hi, float* w_lo, int O, int I, int k, int for_dgrad,
                 cudaStream_t stream);
+// same layouts as __half hi/lo of w * 2^kF16WeightScaleLog2 (3xFP16 operands of conv_tc5.cu)
+int weight_prep_f16(const float* w_oihw, void* w_hi, void* w_lo, int O, int I, int k, int for_dgrad,
+                    cudaStream_t stream);
 
 // ---- loss.cu : fused FPD loss + gradient ----
 // out_s: S pointers to NHWC [B,h,w,J] student heat-maps; target NCHW [B,J,h,w]; teacher NHWC [B,h,w,J] or null;

@@ -93,7 +93,7 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     tma_prefetch_desc(&tm_g_hi);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&ready_bar[s], kTransformThreads);
+      mbar_init(&ready_bar[s], kTransformThreads / 32);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(done_bar, 1);
@@ -259,7 +259,8 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
         if (split) sts128(addr + (uint32_t)half_bytes, l);
       }
       fence_proxy_async_smem();
-      mbar_arrive(&ready_bar[s]);
+      __syncwarp();                       // one arrival per warp: 256 per-thread arrivals on one barrier serialise
+      if (lane == 0) mbar_arrive(&ready_bar[s]);
     }
   }
 

@@ -108,25 +108,45 @@ class BNRef:
 
 
 class PreparedWeights:
-    """Tensor-core operand forms of every conv weight: [tap][O][I] hi/lo (+ flipped/transposed for dgrad)."""
+    """Tensor-core operand forms of the conv weights, prepared on first use within a forward (student: every step,
+    inside the captured graph; frozen teacher: once, cached with the eval context):
+    [tap][O][I] hi/lo (+ flipped/transposed for dgrad). Forward operands are __half pairs (3xFP16, csrc/conv_tc5.cu)
+    where that kernel takes the shape, fp32 containers holding tf32 values otherwise."""
 
-    def __init__(self, convs, passes, need_dgrad):
-        self.fwd = {}
-        self.dgrad = {}
-        split = passes == 3
-        for c in convs:
-            w = c.weight.detach()
-            kpad = c.im2col_kpad
-            if kpad:
-                # OIHW -> [Cout][(kh,kw,ci)] zero-padded to kpad, as a 1x1 conv weight
-                w2 = torch.zeros((c.cout, kpad, 1, 1), dtype=torch.float32, device=w.device)
-                w2[:, :c.cin * c.k * c.k, 0, 0] = w.permute(0, 2, 3, 1).reshape(c.cout, -1)
-                self.fwd[c.name] = ops.weight_prep(w2, for_dgrad=False, split=split)
-                continue
-            if c.tc_fwd:
-                self.fwd[c.name] = ops.weight_prep(w, for_dgrad=False, split=split)
-            if need_dgrad and c.tc_dgrad:
-                self.dgrad[c.name] = ops.weight_prep(w, for_dgrad=True, split=split)
+    def __init__(self, passes):
+        self.split = passes == 3
+        self._fwd = {}
+        self._dgrad = {}
+
+    def fwd(self, c, H, W):
+        """-> (w_hi, w_lo, use_h): use_h selects ops.conv2d_tc_h (generation-5 kernel) over the TS kernel."""
+        e = self._fwd.get(c.name)
+        if e is not None:
+            return e
+        w = c.weight.detach()
+        k, cin = c.k, c.cin
+        kpad = c.im2col_kpad
+        if kpad:
+            # OIHW -> [Cout][(kh,kw,ci)] zero-padded to kpad, as a 1x1 conv weight
+            w2 = torch.zeros((c.cout, kpad, 1, 1), dtype=torch.float32, device=w.device)
+            w2[:, :c.cin * c.k * c.k, 0, 0] = w.permute(0, 2, 3, 1).reshape(c.cout, -1)
+            w, k, cin = w2, 1, kpad
+        if FUSED_FWD and self.split and ops.CONV_F16 and ops.conv2d_tc_h_supported(cin, c.cout, k, H, W, True):
+            hi, lo = ops.weight_prep_f16(w, for_dgrad=False, split=True)
+            e = (hi, lo, True)
+        else:
+            hi, lo = ops.weight_prep(w, for_dgrad=False, split=self.split)
+            e = (hi, lo, FUSED_FWD and ops.conv2d_tc_h_supported(cin, c.cout, k, H, W, False))
+        self._fwd[c.name] = e
+        return e
+
+    def dgrad(self, c, H, W):
+        e = self._dgrad.get(c.name)
+        if e is None:
+            hi, lo = ops.weight_prep(c.weight.detach(), for_dgrad=True, split=self.split)
+            e = (hi, lo, FUSED_DGRAD and ops.conv2d_tc_h_supported(c.cout, c.cin, c.k, H, W, False))
+            self._dgrad[c.name] = e
+        return e
 
 
 class Engine:
@@ -157,7 +177,7 @@ class Engine:
         key = self._param_version()
         if self._eval_cache is None or self._eval_cache_key != key:
             passes = precision_passes()
-            w = PreparedWeights(self.convs.values(), passes, need_dgrad=False)
+            w = PreparedWeights(passes)
             affine = {}
             for name, b in self.bns.items():
                 m = b.mod
@@ -235,8 +255,9 @@ class Engine:
         kpad = c.im2col_kpad if bn_name is None else 0
         if kpad:
             cols = ops.im2col(x.data, c.k, c.stride, c.pad, kpad)
-            w_hi, w_lo = ctx.weights.fwd[conv_name]
-            out = Var(ops.conv2d_tc_fused(cols, w_hi, w_lo, 1, bias=bias, residual=res))
+            w_hi, w_lo, use_h = ctx.weights.fwd(c, cols.shape[1], cols.shape[2])
+            conv_fn = ops.conv2d_tc_h if use_h else ops.conv2d_tc_fused
+            out = Var(conv_fn(cols, w_hi, w_lo, 1, bias=bias, residual=res))
             if ctx.tape is not None:
                 def bwd_stem():
                     dy = out.grad
@@ -255,11 +276,12 @@ class Engine:
                 ctx.tape.append(bwd_stem)
             return out
         if c.tc_fwd:
-            w_hi, w_lo = ctx.weights.fwd[conv_name]
+            w_hi, w_lo, use_h = ctx.weights.fwd(c, x.data.shape[1], x.data.shape[2])
             if FUSED_FWD:
-                # BN-apply + ReLU + tf32 split happen inside the conv kernel (no separate HBM pass)
-                y = ops.conv2d_tc_fused(x.data, w_hi, w_lo, c.k, mean=mean, scale=scale, shift=shift, relu=relu,
-                                        bias=bias, residual=res)
+                # BN-apply + ReLU + operand split happen inside the conv kernel (no separate HBM pass)
+                conv_fn = ops.conv2d_tc_h if use_h else ops.conv2d_tc_fused
+                y = conv_fn(x.data, w_hi, w_lo, c.k, mean=mean, scale=scale, shift=shift, relu=relu, bias=bias,
+                            residual=res)
             else:
                 a_hi, a_lo = ops.affine_act_split(x.data, scale, shift, relu, split=split, mean=mean)
                 y = ops.conv2d_tc(a_hi, a_lo, w_hi, w_lo, c.k, bias=bias, residual=res)
@@ -309,9 +331,9 @@ class Engine:
                     return
                 # ---- data gradient w.r.t. the conv input a = act(bn(x))
                 if c.tc_dgrad:
-                    wd_hi, wd_lo = ctx.weights.dgrad[conv_name]
+                    wd_hi, wd_lo, use_h = ctx.weights.dgrad(c, dy.shape[1], dy.shape[2])
                     if FUSED_DGRAD:
-                        da = ops.conv2d_tc_fused(dy, wd_hi, wd_lo, c.k)
+                        da = (ops.conv2d_tc_h if use_h else ops.conv2d_tc_fused)(dy, wd_hi, wd_lo, c.k)
                     else:
                         da = ops.conv2d_tc(dy_hi, dy_lo, wd_hi, wd_lo, c.k)
                 else:
@@ -407,12 +429,12 @@ class Engine:
         ctx.passes = precision_passes()
         ctx.tape = [] if record_tape else None
         if training:
-            ctx.weights = PreparedWeights(self.convs.values(), ctx.passes, need_dgrad=record_tape)
+            ctx.weights = PreparedWeights(ctx.passes)
             ctx.affine = None
         else:
             w, affine = self._eval_prepared()
             if record_tape:
-                w = PreparedWeights(self.convs.values(), ctx.passes, need_dgrad=True)
+                w = PreparedWeights(ctx.passes)
             ctx.weights, ctx.affine = w, affine
         outs = self.run_network(ctx, img_nchw.contiguous().float())
         if ctx.nbt:

@@ -150,6 +150,40 @@ def conv2d_tc_fused(x, w_hi, w_lo, ksize, mean=None, scale=None, shift=None, rel
     return y
 
 
+CONV_H = os.environ.get("FPD_CONV_H", "1") != "0"          # generation-5 kernel (halo reuse) where it supports the shape
+CONV_F16 = os.environ.get("FPD_CONV_F16", "1") != "0"      # 3xFP16 operands for the forward convolutions
+
+
+def conv2d_tc_h_supported(cin, cout, k, H, W, f16):
+    return CONV_H and bool(N.lib().fpd_conv2d_tc_h_supported(cin, cout, k, H, W, int(f16)))
+
+
+def weight_prep_f16(w_oihw, for_dgrad=False, split=True):
+    """__half hi/lo of w * 2^8 (3xFP16 operands of conv2d_tc_h(f16=True)); layouts as weight_prep."""
+    _chk(w_oihw, "w")
+    O, I, k, _ = w_oihw.shape
+    shape = (k * k, I, O) if for_dgrad else (k * k, O, I)
+    hi = torch.empty(shape, dtype=torch.float16, device=w_oihw.device)
+    lo = torch.empty_like(hi) if split else None
+    N.check(N.lib().fpd_weight_prep_f16(_p(w_oihw), _p(hi), _p(lo), O, I, k, int(for_dgrad), _stream()),
+            "weight_prep_f16")
+    return hi, lo
+
+
+def conv2d_tc_h(x, w_hi, w_lo, ksize, mean=None, scale=None, shift=None, relu=False, bias=None, residual=None,
+                relu_mask=None, out=None, out_scale=1.0):
+    """y = conv(relu?((x-mean)*scale+shift)) on the generation-5 kernel (csrc/conv_tc5.cu). The operand precision
+    follows the weight dtype: float16 hi/lo -> 3xFP16 (kind::f16), float32 containers -> 3xTF32."""
+    B, H, W, Cin = x.shape
+    Cout = w_hi.shape[1]
+    f16 = w_hi.dtype == torch.float16
+    y = out if out is not None else torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
+    N.check(N.lib().fpd_conv2d_tc_h(_p(x), _p(mean), _p(scale), _p(shift), int(relu), _p(w_hi), _p(w_lo), int(f16),
+                                    _p(bias), _p(residual), _p(relu_mask), _p(y), float(out_scale), B, H, W, Cin, Cout,
+                                    ksize, _stream()), "conv2d_tc_h")
+    return y
+
+
 def conv2d_simt_fwd(x, w_oihw, bias=None, residual=None, stride=1, pad=0, out=None):
     B, H, W, Cin = x.shape
     Cout, _, k, _ = w_oihw.shape

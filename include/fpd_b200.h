@@ -85,6 +85,25 @@ int fpd_conv2d_tc_g(const float* x, const float* pre_mean, const float* pre_scal
                     const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
                     int ksize, fpd_stream_t stream);
 
+/* Generation-5 fused convolution (csrc/conv_tc5.cu), same contract as fpd_conv2d_tc_fused. 3x3: the activation tile is
+ * fetched with its halo and transformed once per channel block, the nine taps are shifted on-chip copies into tensor
+ * memory. f16 = 1 selects 3xFP16 operands (x = hi + lo in fp16, tcgen05.mma kind::f16, fp32 accumulate): w_hi / w_lo
+ * are then the __half arrays of fpd_weight_prep_f16; f16 = 0: fp32 containers of fpd_weight_prep (3xTF32).
+ * w_lo NULL => single pass. Replaces nn.Conv2d after BatchNorm2d + ReLU, lib/models/hourglass.py:34-44. */
+int fpd_conv2d_tc_h_supported(int Cin, int Cout, int ksize, int H, int W, int f16);
+int fpd_conv2d_tc_h(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
+                    int pre_relu, const void* w_hi, const void* w_lo, int f16, const float* bias,
+                    const float* residual, const float* relu_mask, float* y, float out_scale, int B, int H, int W,
+                    int Cin, int Cout, int ksize, fpd_stream_t stream);
+/* Profiling aid: when device_buf is non-NULL every following fpd_conv2d_tc_h launch writes, per CTA, 16 int64 stall
+ * counters (cycles each warp role spent waiting on each pipeline barrier) to device_buf[blockIdx.x * 16 ...]; NULL
+ * switches it off (the default). Not thread-safe; intended for tools/diag_conv_h.py only. */
+int fpd_conv2d_tc_h_set_profile_buffer(long long* device_buf);
+/* OIHW fp32 -> __half hi/lo of w * 2^8 in the layouts of fpd_weight_prep (w_lo may be NULL); the 2^-8 is applied by
+ * fpd_conv2d_tc_h. */
+int fpd_weight_prep_f16(const float* w_oihw, void* w_hi, void* w_lo, int O, int I, int k, int for_dgrad,
+                        fpd_stream_t stream);
+
 /* Tensor-core weight gradient: dw_oihw[Cout,Cin,k,k] = scale * sum_pixels dy (x) a(tap-shifted). */
 int fpd_conv2d_wgrad_tc_supported(int Cin, int Cout, int ksize);
 size_t fpd_conv2d_wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize);

@@ -125,6 +125,53 @@ def test_conv2d_tc_ts_wide_output_slices(shape):
     assert relerr(nchw(y), ref) < 2e-5
 
 
+@pytest.mark.parametrize("shape", CONV_TC_SHAPES + CONV_TS_WIDE_SHAPES + [(2, 64, 64, 160, 32, 1), (5, 16, 16, 256, 128, 3)])
+@pytest.mark.parametrize("passes", [3, 1])
+@pytest.mark.parametrize("f16", [False, True])
+def test_conv2d_tc_h(shape, passes, f16):
+    """Generation-5 kernel (halo reuse; 3xFP16 or 3xTF32 operands) vs torch fp32: conv(relu(bn_affine(x))) + bias +
+    residual, and the identity pre-op form used for dgrad."""
+    B, H, W, Cin, Cout, k = shape
+    o = ops()
+    if not o.N.lib().fpd_conv2d_tc_h_supported(Cin, Cout, k, H, W, int(f16)):
+        pytest.skip("shape not taken by conv_tc_h (f16=%s)" % f16)
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g) * 2 + 0.5
+    mean = torch.randn(Cin, device="cuda", generator=g)
+    scale = torch.rand(Cin, device="cuda", generator=g) + 0.5
+    shift = torch.randn(Cin, device="cuda", generator=g) * 0.5
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * (1.0 / (Cin * k * k) ** 0.5)
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(B, Cout, H, W, device="cuda", generator=g)
+    a = F.relu((x - mean.view(1, -1, 1, 1)) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    ref = F.conv2d(a, w, bias, padding=k // 2) + res
+    prep = o.weight_prep_f16 if f16 else o.weight_prep
+    w_hi, w_lo = prep(w, split=(passes == 3))
+    y = o.conv2d_tc_h(nhwc(x), w_hi, w_lo, k, mean=mean, scale=scale, shift=shift, relu=True, bias=bias,
+                      residual=nhwc(res))
+    y2 = o.conv2d_tc_h(nhwc(x), w_hi, w_lo, k)
+    ref2 = F.conv2d(x, w, None, padding=k // 2)
+    torch.cuda.synchronize()
+    tol = 3e-5 if passes == 3 else 3e-3   # K up to 3456: the fp32 torch reference itself carries ~1e-5
+    assert relerr(nchw(y), ref) < tol, "conv_tc_h %s passes=%d f16=%s rel err %.3e" % (shape, passes, f16,
+                                                                                        relerr(nchw(y), ref))
+    assert relerr(nchw(y2), ref2) < tol
+
+
+def test_conv2d_tc_h_f16_small_and_large_magnitudes():
+    """3xFP16 keeps fp32-grade accuracy away from the fp16 range limits: activations of magnitude 1e-2 .. 1e3."""
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(99)
+    for mag in (1e-2, 1.0, 1e3):
+        x = torch.randn(2, 64, 32, 32, device="cuda", generator=g) * mag
+        w = torch.randn(64, 64, 3, 3, device="cuda", generator=g) * (1.0 / 24.0)
+        ref = F.conv2d(F.relu(x), w, None, padding=1)
+        w_hi, w_lo = o.weight_prep_f16(w)
+        y = o.conv2d_tc_h(nhwc(x), w_hi, w_lo, 3, relu=True)
+        torch.cuda.synchronize()
+        assert relerr(nchw(y), ref) < (2e-4 if mag < 0.1 else 2e-5), "mag %g: %.3e" % (mag, relerr(nchw(y), ref))
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 64, 64, 64, 3), (2, 32, 32, 128, 64, 1), (4, 8, 8, 64, 128, 1)])
 def test_conv2d_tc_dgrad_with_relu_mask(shape):
     B, H, W, Cin, Cout, k = shape
