@@ -196,7 +196,11 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   float* s_scale = s_mean + kParamFloats;
   float* s_shift = s_scale + kParamFloats;
 
-  const int warp = threadIdx.x >> 5;
+  // warp index made provably warp-uniform (shfl broadcast): the single-thread TMA / MMA issue code below then keeps its
+  // descriptors in uniform registers. With a threadIdx-derived `if (lane == 0)` around the whole role ptxas wraps every
+  // UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall loop (~100 cycles per MMA, measured: the issuing
+  // thread, not the tensor core, bounded the kernel).
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -232,7 +236,8 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // whole warp runs the loop; one elected lane arms the barrier and issues the bulk-tensor copies
+    {
       int rs = 0, ws = 0;
       uint32_t rph = 0, wph = 0;
       const uint32_t w_tx = (uint32_t)p.w_stage_bytes;
@@ -244,16 +249,19 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const TileCoord t = tile_coord(p, tile);
         const int nbox = (kBoxes == 2 && p.Cin - cb * kCB > 32) ? 2 : 1;
         timed_wait(&raw_empty[rs], rph ^ 1, prof, c_rempty);
-        uint8_t* dst = raw_base + (size_t)rs * p.raw_stage_bytes;
-        const uint32_t box_tx = (uint32_t)((halo ? p.halo_px : kTileM) * 128);
-        if (p.dbg & 4) {
-          mbar_arrive(&raw_full[rs]);
-        } else {
-          mbar_expect_tx(&raw_full[rs], box_tx * (uint32_t)nbox);
-          const int wc = halo ? t.w0 - 1 : t.w0, hc = halo ? t.h0 - 1 : t.h0;
-          for (int b = 0; b < nbox; ++b)
-            tma_load_4d(dst + (size_t)b * p.raw_box_bytes, &tm_x, &raw_full[rs], cb * kCB + b * 32, wc, hc, t.n0);
+        if (elect_one()) {
+          uint8_t* dst = raw_base + (size_t)rs * p.raw_stage_bytes;
+          const uint32_t box_tx = (uint32_t)((halo ? p.halo_px : kTileM) * 128);
+          if (p.dbg & 4) {
+            mbar_arrive(&raw_full[rs]);
+          } else {
+            mbar_expect_tx(&raw_full[rs], box_tx * (uint32_t)nbox);
+            const int wc = halo ? t.w0 - 1 : t.w0, hc = halo ? t.h0 - 1 : t.h0;
+            tma_load_4d(dst, &tm_x, &raw_full[rs], cb * kCB, wc, hc, t.n0);
+            if (nbox == 2) tma_load_4d(dst + p.raw_box_bytes, &tm_x, &raw_full[rs], cb * kCB + 32, wc, hc, t.n0);
+          }
         }
+        __syncwarp();
         rs = (rs + 1 == p.raw_stages) ? 0 : rs + 1;
         rph ^= (rs == 0);
       };
@@ -268,28 +276,32 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const int n0w = (tile % p.n_tiles) * p.nt;
         for (int tap = 0; tap < p.taps; ++tap) {
           timed_wait(&w_empty[ws], wph ^ 1, prof, c_wempty);
-          uint8_t* st = w_base + (size_t)ws * p.w_stage_bytes;
-          if (p.dbg & 2) {
-            mbar_arrive(&w_full[ws]);
-          } else {
-            mbar_expect_tx(&w_full[ws], w_tx);
-            tma_load_3d(st, &tm_w_hi, &w_full[ws], cb * kCB, n0w, tap);
-            if (split) tma_load_3d(st + p.w_tile_bytes, &tm_w_lo, &w_full[ws], cb * kCB, n0w, tap);
+          if (elect_one()) {
+            uint8_t* st = w_base + (size_t)ws * p.w_stage_bytes;
+            if (p.dbg & 2) {
+              mbar_arrive(&w_full[ws]);
+            } else {
+              mbar_expect_tx(&w_full[ws], w_tx);
+              tma_load_3d(st, &tm_w_hi, &w_full[ws], cb * kCB, n0w, tap);
+              if (split) tma_load_3d(st + p.w_tile_bytes, &tm_w_lo, &w_full[ws], cb * kCB, n0w, tap);
+            }
           }
+          __syncwarp();
           ws = (ws + 1 == p.w_stages) ? 0 : ws + 1;
           wph ^= (ws == 0);
           if (tap == pre_tap && nvalid) issue_raw(ntile, ncb_);
         }
         tile = ntile; cb = ncb_; valid = nvalid;
       }
-      if (prof) {
+      if (prof && lane == 0) {
         long long* o = p.prof + (size_t)blockIdx.x * 16;
         o[0] = c_wempty; o[1] = c_rempty; o[2] = clock64() - c_start;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop (waits included); one elected lane issues the MMAs and commits.
+    {
       const uint32_t idesc = kF16 ? umma_idesc_f16(kTileM, (uint32_t)p.nt) : umma_idesc_tf32(kTileM, (uint32_t)p.nt, 0, 0);
       uint32_t tile_iter = 0;
       int ws = 0, as_ = 0;
@@ -297,50 +309,58 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       const bool prof = p.prof != nullptr;
       long long c_wfull = 0, c_aready = 0, c_tempty = 0;
       const long long c_start = prof ? clock64() : 0;
+      const uint32_t w_base_a = smem_u32(w_base);
+      const int ksteps = p.ncb * p.taps;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
         const uint32_t acs = p.acc_stages == 2 ? (tile_iter & 1) : 0u;
         const uint32_t acph = (p.acc_stages == 2 ? (tile_iter >> 1) : tile_iter) & 1;
         timed_wait(&tmem_empty[acs], acph ^ 1, prof, c_tempty);
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + acs * (uint32_t)p.tmem_cols;
-        const int ksteps = p.ncb * p.taps;
         for (int kb = 0; kb < ksteps; ++kb) {
           timed_wait(&w_full[ws], wph, prof, c_wfull);
           timed_wait(&a_ready[as_], aph_, prof, c_aready);
           tc_fence_after_sync();
-          const uint32_t b_hi = smem_u32(w_base + (size_t)ws * p.w_stage_bytes);
-          const uint32_t b_lo = b_hi + (uint32_t)p.w_tile_bytes;
-          const uint32_t ta_hi = tmem_base + (uint32_t)p.a_col0 + (uint32_t)as_ * 64u;
-          const uint32_t ta_lo = ta_hi + 32u;
+          if (elect_one()) {
+            const uint32_t b_hi = w_base_a + (uint32_t)ws * (uint32_t)p.w_stage_bytes;
+            const uint64_t db_hi0 = umma_desc_sw128(b_hi, 16, 1024);
+            const uint64_t db_lo0 = umma_desc_sw128(b_hi + (uint32_t)p.w_tile_bytes, 16, 1024);
+            const uint32_t ta_hi = tmem_base + (uint32_t)p.a_col0 + (uint32_t)as_ * 64u;
+            const uint32_t ta_lo = ta_hi + 32u;
+            if (!(p.dbg & 1)) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            if (p.dbg & 1) break;
-            const uint64_t db_hi = umma_desc_sw128(b_hi + ks * 32, 16, 1024);
-            uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
-            if (split) {
-              const uint64_t db_lo = umma_desc_sw128(b_lo + ks * 32, 16, 1024);
-              if (kF16) {
-                umma_f16_ts(tmem_d, ta_lo + ks * 8, db_hi, idesc, acc);
-                umma_f16_ts(tmem_d, ta_hi + ks * 8, db_lo, idesc, 1u);
-              } else {
-                umma_tf32_ts(tmem_d, ta_lo + ks * 8, db_hi, idesc, acc);
-                umma_tf32_ts(tmem_d, ta_hi + ks * 8, db_lo, idesc, 1u);
+              for (int ks = 0; ks < 4; ++ks) {
+                // +32 bytes along K inside the 128-byte swizzle row = +2 in the (address >> 4) start field
+                const uint64_t db_hi = db_hi0 + (uint64_t)(ks * 2);
+                uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
+                if (split) {
+                  const uint64_t db_lo = db_lo0 + (uint64_t)(ks * 2);
+                  if (kF16) {
+                    umma_f16_ts(tmem_d, ta_lo + ks * 8, db_hi, idesc, acc);
+                    umma_f16_ts(tmem_d, ta_hi + ks * 8, db_lo, idesc, 1u);
+                  } else {
+                    umma_tf32_ts(tmem_d, ta_lo + ks * 8, db_hi, idesc, acc);
+                    umma_tf32_ts(tmem_d, ta_hi + ks * 8, db_lo, idesc, 1u);
+                  }
+                  acc = 1u;
+                }
+                if (kF16) umma_f16_ts(tmem_d, ta_hi + ks * 8, db_hi, idesc, acc);
+                else umma_tf32_ts(tmem_d, ta_hi + ks * 8, db_hi, idesc, acc);
               }
-              acc = 1u;
             }
-            if (kF16) umma_f16_ts(tmem_d, ta_hi + ks * 8, db_hi, idesc, acc);
-            else umma_tf32_ts(tmem_d, ta_hi + ks * 8, db_hi, idesc, acc);
+            umma_commit(&w_empty[ws]);
+            umma_commit(&a_empty[as_]);
           }
-          umma_commit(&w_empty[ws]);
-          umma_commit(&a_empty[as_]);
+          __syncwarp();
           ws = (ws + 1 == p.w_stages) ? 0 : ws + 1;
           wph ^= (ws == 0);
           as_ = (as_ + 1 == p.a_stages) ? 0 : as_ + 1;
           aph_ ^= (as_ == 0);
         }
-        umma_commit(&tmem_full[acs]);
+        if (elect_one()) umma_commit(&tmem_full[acs]);
+        __syncwarp();
       }
-      if (prof) {
+      if (prof && lane == 0) {
         long long* o = p.prof + (size_t)blockIdx.x * 16;
         o[3] = c_wfull; o[4] = c_aready; o[5] = c_tempty; o[6] = clock64() - c_start;
       }

@@ -81,7 +81,10 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   float* s_scale = s_mean + kMaxCin;
   float* s_shift = s_scale + kMaxCin;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index made provably warp-uniform so the elected-lane TMA / MMA issue code keeps its descriptors in uniform
+  // registers (a threadIdx-derived `if (lane == 0)` region makes ptxas wrap every UTCHMMA / UTMALDG in an
+  // ELECT + R2UR.BROADCAST waterfall loop, ~100 cycles per MMA -- see conv_tc5.cu)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int g = blockIdx.x % p.groups;
   const int sp = blockIdx.x / p.groups;
   const int kt0 = sp * p.kt_per_split;
@@ -119,12 +122,13 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   const bool split = p.passes == 3;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < nkt; ++i, s = (s + 1 == p.stages ? 0 : s + 1), ph ^= (s == 0)) {
         const int kt = kt0 + i;
         mbar_wait(&empty_bar[s], ph ^ 1);
+        if (!elect_one()) { __syncwarp(); continue; }
         const int tw = kt % p.tiles_w, th = (kt / p.tiles_w) % p.tiles_h, tn = kt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
         uint8_t* st = smem + (size_t)s * p.stage_bytes;
@@ -145,16 +149,18 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
           uint8_t* dst = st + (4 + j) * kBoxBytes;
           tma_load_4d(dst, p.mode_b ? &tm_a_hi : &tm_g_hi, &full_bar[s], j * 32, w0, h0, n0);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = umma_idesc_tf32(128, (uint32_t)p.N, 1, 1);  // both operands MN-major
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < nkt; ++i, s = (s + 1 == p.stages ? 0 : s + 1), ph ^= (s == 0)) {
         mbar_wait(&ready_bar[s], ph);   // transform done (implies the TMA bytes have landed)
         tc_fence_after_sync();
+        if (!elect_one()) { __syncwarp(); continue; }
         const uint32_t m_hi = smem_u32(smem + (size_t)s * p.stage_bytes);
         const uint32_t n_hi = m_hi + 4 * kBoxBytes;
         const uint32_t m_lo = m_hi + half_bytes;
@@ -175,8 +181,10 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
           umma_tf32(tmem_base, dm_hi, dn_hi, idesc, acc);
         }
         umma_commit(&empty_bar[s]);
+        __syncwarp();
       }
-      umma_commit(done_bar);
+      if (elect_one()) umma_commit(done_bar);
+      __syncwarp();
     }
   } else if (warp < 6) {
     const int q = warp & 3;
