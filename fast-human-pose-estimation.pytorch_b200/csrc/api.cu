@@ -134,6 +134,24 @@ int fpd_conv2d_tc_h(const float* x, const float* pre_mean, const float* pre_scal
                           out_scale, B, H, W, Cin, Cout, ksize, device_sm_count(), S(stream));
 }
 
+int fpd_channel_sum_fused(const float* dy, int64_t P, int C, float scale, float* out, float* amax_scale,
+                          void* workspace, size_t workspace_bytes, unsigned int* counter, fpd_stream_t stream) {
+  return channel_sum_fused(dy, P, C, scale, out, amax_scale, workspace, workspace_bytes, counter, S(stream));
+}
+int fpd_bn_bwd_reduce_fused(const float* da, const float* x, const float* mean, const float* invstd,
+                            const float* scale, const float* shift, int relu, int64_t P, int C, float* sums,
+                            void* workspace, size_t workspace_bytes, unsigned int* counter, fpd_stream_t stream) {
+  return bn_bwd_reduce_fused(da, x, mean, invstd, scale, shift, relu, P, C, sums, workspace, workspace_bytes, counter,
+                             S(stream));
+}
+int fpd_bn_stats_fused(const float* x, int64_t P, int C, const float* gamma, const float* beta, float eps,
+                       float momentum, float* running_mean, float* running_var, float* mean, float* var_biased,
+                       float* scale, float* shift, float* invstd, void* workspace, size_t workspace_bytes,
+                       unsigned int* counter, fpd_stream_t stream) {
+  return bn_stats_fused(x, P, C, gamma, beta, eps, momentum, running_mean, running_var, mean, var_biased, scale, shift,
+                        invstd, workspace, workspace_bytes, counter, S(stream));
+}
+
 int fpd_conv2d_tc_h_set_profile_buffer(long long* device_buf) {
   conv_tc_h_set_profile_buffer(device_buf);
   return FPD_OK;

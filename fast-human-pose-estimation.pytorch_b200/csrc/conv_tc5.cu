@@ -395,6 +395,25 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         pixoff[it] = (uint32_t)((((size_t)pn * p.H + ph_) * p.W + pw) * (size_t)p.Cout + (size_t)t.n0w);
       }
       if (p.dbg & 16) vmask = 0;
+      // Pull the residual rows towards the L2 one tile ahead (this tile's too, the first time): the loads below then
+      // cost an L2 hit instead of an HBM round trip per 32-column group, which was what paced the 1x1 convolutions
+      // (epilogue busy 6 us per tile against 3 us of HBM time, tools/diag_conv_h.py --stalls).
+      if (p.residual && !(p.dbg & 16) && ch == 0) {
+        for (int which = (tile_iter == 0 ? 0 : 1); which < 2; ++which) {
+          const int tl = tile + which * (int)gridDim.x;
+          if (tl >= p.num_tiles) break;
+          const TileCoord tp = tile_coord(p, tl);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int m = q * 32 + it * 4 + sub;
+            const int pn = tp.n0 + m / (p.bw * p.bh);
+            if (pn >= p.B) continue;
+            const size_t off = (((size_t)pn * p.H + tp.h0 + (m / p.bw) % p.bh) * p.W + tp.w0 + (m % p.bw)) * (size_t)p.Cout +
+                               (size_t)tp.n0w;
+            for (int c = 0; c < p.nt; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + off + c));
+          }
+        }
+      }
       timed_wait(&tmem_full[acs], acph, prof, c_tfull);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + acs * (uint32_t)p.tmem_cols + ((uint32_t)(q * 32) << 16);

@@ -23,14 +23,17 @@ struct RedGeom {
   int64_t rows_per_block;
 };
 
-inline RedGeom red_geom(int64_t P, int C) {
+inline RedGeom red_geom(int64_t P, int C, int max_blocks = kMaxRedBlocks);
+// the single-launch (last block finishes) forms keep the second stage short: one wave of blocks
+constexpr int kMaxFusedRedBlocks = 148;
+inline RedGeom red_geom(int64_t P, int C, int max_blocks) {
   RedGeom g;
   g.L = C / 4;
   g.R = kRedThreads / g.L;
   if (g.R < 1) g.R = 1;
   int64_t want = (P + (int64_t)g.R * 4 - 1) / ((int64_t)g.R * 4);
   if (want < 1) want = 1;
-  g.nblocks = (int)(want < kMaxRedBlocks ? want : kMaxRedBlocks);
+  g.nblocks = (int)(want < max_blocks ? want : max_blocks);
   g.rows_per_block = (P + g.nblocks - 1) / g.nblocks;
   // round rows_per_block up to a multiple of R so chunk boundaries are uniform
   g.rows_per_block = (g.rows_per_block + g.R - 1) / g.R * g.R;
@@ -167,13 +170,105 @@ __global__ void bn_finalize_kernel(const float* __restrict__ mean, const float* 
   }
 }
 
+// "Last block finishes" form of a two-stage reduction: every block publishes its partial, takes a ticket, and the
+// block that draws the last ticket runs the (fixed-order, hence deterministic) second stage. One launch instead of two
+// or three; the ticket counter must be zero on entry and is left zero (self-resetting, CUDA-graph safe). Returns true in
+// the finishing block only.
+__device__ __forceinline__ bool last_block_ticket(unsigned int* counter) {
+  __shared__ bool s_last;
+  __threadfence();   // release this block's partials
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) __threadfence();   // acquire the other blocks' partials
+  return s_last;
+}
+
+struct BnFinalize {
+  const float* gamma; const float* beta; float eps; float momentum;
+  float* mean; float* var; float* scale; float* shift; float* invstd; float* rmean; float* rvar;
+};
+
+// Second stage of the BN statistics + the BatchNorm finalize of one consuming module in ONE kernel (was two): per
+// channel, mean = sum_b n_b mean_b / P, then M2 = sum_b M2_b + n_b (mean_b - mean)^2 over the block partials of
+// bn_stats_partial_kernel, in fp64 and a fixed order (deterministic; no division inside the loops, unlike the sequential
+// Chan merge of bn_stats_final_kernel whose fp64 divide chain cost ~7 us per launch). One warp per 4 channels.
+// Reference semantics: nn.BatchNorm2d in train mode incl. the running-statistics update (lib/models/hourglass.py:18-26).
+__global__ void bn_stats_final_finalize_kernel(const double* __restrict__ part, int nblocks, int64_t rows_per_block,
+                                               int64_t P, int C, BnFinalize fz) {
+  const int lane = threadIdx.x & 31;
+  const int c0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4;
+  if (c0 >= C) return;
+  double sw[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+  for (int b = lane; b < nblocks; b += 32) {
+    int64_t r0 = (int64_t)b * rows_per_block, r1 = r0 + rows_per_block;
+    if (r1 > P) r1 = P;
+    const double nb = (double)(r1 > r0 ? r1 - r0 : 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (c0 + k < C) sw[k] += nb * part[((size_t)b * C + c0 + k) * 2 + 0];
+  }
+  double mu[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) mu[k] = warp_sum(sw[k]) / (double)P;
+  double m2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+  for (int b = lane; b < nblocks; b += 32) {
+    int64_t r0 = (int64_t)b * rows_per_block, r1 = r0 + rows_per_block;
+    if (r1 > P) r1 = P;
+    const double nb = (double)(r1 > r0 ? r1 - r0 : 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (c0 + k < C) {
+        const double d = part[((size_t)b * C + c0 + k) * 2 + 0] - mu[k];
+        m2[k] += part[((size_t)b * C + c0 + k) * 2 + 1] + nb * d * d;
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double m2t = warp_sum(m2[k]);
+    const int c = c0 + k;
+    if (lane == 0 && c < C) {
+      const float m = (float)mu[k], v = (float)(m2t / (double)P);
+      fz.mean[c] = m;
+      fz.var[c] = v;
+      const float invstd = (float)(1.0 / sqrt((double)v + (double)fz.eps));
+      const float g = fz.gamma ? fz.gamma[c] : 1.f, b = fz.beta ? fz.beta[c] : 0.f;
+      fz.scale[c] = g * invstd;
+      fz.shift[c] = b;   // centred form: y = (x - mean) * scale + shift
+      if (fz.invstd) fz.invstd[c] = invstd;
+      if (fz.rmean) {
+        fz.rmean[c] = (1.f - fz.momentum) * fz.rmean[c] + fz.momentum * m;
+        const float unbiased = P > 1 ? v * ((float)P / (float)(P - 1)) : v;
+        fz.rvar[c] = (1.f - fz.momentum) * fz.rvar[c] + fz.momentum * unbiased;
+      }
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // generic per-channel sum reductions (NV sums per element), deterministic two-stage
 // -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void write_amax_scale(float m, float* amax_scale) {
+  // power-of-two scale that puts max|v| into [2^14, 2^15): fp16 hi/lo operands of v * S then keep every element to within
+  // 2^-39 of the largest one (csrc/conv_tc5.cu in_scale). Zero / non-finite maxima -> no scaling.
+  float S = 1.f;
+  if (m > 0.f && m < 3.0e38f) {
+    int e;
+    frexpf(m, &e);            // m = f * 2^e, f in [0.5, 1)
+    S = ldexpf(1.f, 15 - e);  // m * S in [2^14, 2^15)
+  }
+  amax_scale[0] = S;
+  amax_scale[1] = 1.f / S;
+}
+
 template <int NV, class F>
 __global__ void __launch_bounds__(kRedThreads)
 channel_reduce_partial_kernel(F f, int64_t P, int C, int L, int R, int64_t rows_per_block,
-                              double* __restrict__ part /*[nblocks][NV][C]*/) {
+                              double* __restrict__ part /*[nblocks][NV][C]*/, unsigned int* counter = nullptr,
+                              float out_scale = 1.f, float* __restrict__ out = nullptr,
+                              float* __restrict__ amax_scale /*[2] or null*/ = nullptr) {
   extern __shared__ double sm[];  // [R][NV][C]
   const int tid = threadIdx.x;
   const int cx = tid % L;
@@ -181,6 +276,7 @@ channel_reduce_partial_kernel(F f, int64_t P, int C, int L, int R, int64_t rows_
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
   int64_t row1 = row0 + rows_per_block;
   if (row1 > P) row1 = P;
+  float tmax = 0.f;   // max |v[0]| seen by this thread (used by the fused form's amax output)
   if (ry < R) {
     double acc[NV][4];
 #pragma unroll
@@ -196,6 +292,8 @@ channel_reduce_partial_kernel(F f, int64_t P, int C, int L, int R, int64_t rows_
     for (int64_t r = row0 + ry; r < row1; r += R) {
       float v[NV][4];
       f(r, cx, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tmax = fmaxf(tmax, fabsf(v[0][j]));
 #pragma unroll
       for (int k = 0; k < NV; ++k)
 #pragma unroll
@@ -222,13 +320,62 @@ channel_reduce_partial_kernel(F f, int64_t P, int C, int L, int R, int64_t rows_
     for (int r = 0; r < R; ++r) s += sm[(size_t)r * NV * C + i];
     part[(size_t)blockIdx.x * NV * C + i] = s;
   }
+  // optional max |v| of the first value plane (block maxima live behind the partial sums)
+  float* pmax = reinterpret_cast<float*>(part + (size_t)gridDim.x * NV * C);
+  if (amax_scale) {
+    __shared__ float s_max[kRedThreads / 32];
+    float mx = tmax;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) s_max[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+      float m = s_max[0];
+      for (int w = 1; w < kRedThreads / 32; ++w) m = fmaxf(m, s_max[w]);
+      pmax[blockIdx.x] = m;
+    }
+  }
+  if (counter == nullptr) return;   // two-stage form (the default): channel_reduce_final_kernel follows
+  if (!last_block_ticket(counter)) return;
+  const int nblocks = gridDim.x, n = NV * C, lane = tid & 31;
+  for (int i0 = (tid >> 5) * 4; i0 < n; i0 += (kRedThreads / 32) * 4) {   // 4 outputs per warp iteration: loads in flight
+    double s4[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = lane; b < nblocks; b += 32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (i0 + k < n) s4[k] += __ldcg(&part[(size_t)b * n + i0 + k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double t = warp_sum(s4[k]);
+      if (lane == 0 && i0 + k < n) out[i0 + k] = (float)(t * (double)out_scale);
+    }
+  }
+  if (amax_scale && tid < 32) {
+    float m = 0.f;
+    for (int b = lane; b < nblocks; b += 32) m = fmaxf(m, __ldcg(&pmax[b]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) write_amax_scale(m, amax_scale);
+  }
+  if (tid == 0) *counter = 0u;
 }
 
 // one warp per output value; lanes sum a strided subset of the block partials, then a fixed-order shuffle tree
 __global__ void channel_reduce_final_kernel(const double* __restrict__ part, int nblocks, int n /*NV*C*/,
-                                            float scale, float* __restrict__ out) {
+                                            float scale, float* __restrict__ out,
+                                            float* __restrict__ amax_scale = nullptr) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  if (amax_scale && i == n) {   // one extra warp: block maxima -> operand scale
+    const float* pmax = reinterpret_cast<const float*>(part + (size_t)nblocks * n);
+    float m = 0.f;
+    for (int b = lane; b < nblocks; b += 32) m = fmaxf(m, pmax[b]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) write_amax_scale(m, amax_scale);
+    return;
+  }
   if (i >= n) return;
   double s = 0.0;
   for (int b = lane; b < nblocks; b += 32) s += part[(size_t)b * n + i];
@@ -753,7 +900,35 @@ int add_tensors(const float* a, const float* b, float* out, int64_t n, cudaStrea
 
 size_t channel_reduce_workspace_bytes(int64_t P, int C) {
   RedGeom g = red_geom(P, C);
-  return (size_t)g.nblocks * 2 * C * sizeof(double);
+  return (size_t)g.nblocks * 2 * C * sizeof(double) + (size_t)g.nblocks * sizeof(float);   // + block maxima (fused form)
+}
+
+template <int NV, class F>
+static int run_channel_reduce_fused(F f, int64_t P, int C, float scale, float* out, float* amax_scale, void* workspace,
+                                    size_t ws_bytes, unsigned int* counter, cudaStream_t stream) {
+  // Two launches (partial + final). A single-launch "last block finishes" form exists behind counter != null in the
+  // kernel, but measured ~2x slower on B200 (one wave of blocks starves the main pass of memory parallelism, many blocks
+  // make the one-CTA tail long), so the counter is accepted for ABI stability and ignored.
+  (void)counter;
+  FPD_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "channel reduce: C=%d must be a multiple of 4 in [4,1024]", C);
+  RedGeom g = red_geom(P, C);
+  FPD_REQUIRE(ws_bytes >= (size_t)g.nblocks * NV * C * sizeof(double) + (size_t)g.nblocks * sizeof(float),
+              "channel reduce: workspace too small");
+  const size_t smem = (size_t)g.R * NV * C * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(channel_reduce_partial_kernel<NV, F>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
+  channel_reduce_partial_kernel<NV, F><<<g.nblocks, kRedThreads, smem, stream>>>(
+      f, P, C, g.L, g.R, g.rows_per_block, (double*)workspace, nullptr, scale, out, amax_scale);
+  FPD_LAUNCH_CHECK();
+  const int warps = NV * C + (amax_scale ? 1 : 0);
+  channel_reduce_final_kernel<<<(warps * 32 + 127) / 128, 128, 0, stream>>>((const double*)workspace, g.nblocks, NV * C,
+                                                                       scale, out, amax_scale);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
 }
 
 template <int NV, class F>
@@ -805,6 +980,46 @@ int channel_sum(const float* dy, int64_t P, int C, float scale, float* out, void
   }
   SumFunctor f{dy, C};
   return run_channel_reduce<1>(f, P, C, scale, out, workspace, ws_bytes, stream);
+}
+
+int channel_sum_fused(const float* dy, int64_t P, int C, float scale, float* out, float* amax_scale, void* workspace,
+                      size_t ws_bytes, unsigned int* counter, cudaStream_t stream) {
+  SumFunctor f{dy, C};
+  return run_channel_reduce_fused<1>(f, P, C, scale, out, amax_scale, workspace, ws_bytes, counter, stream);
+}
+
+int bn_bwd_reduce_fused(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
+                        const float* shift, int relu, int64_t P, int C, float* sums, void* workspace, size_t ws_bytes,
+                        unsigned int* counter, cudaStream_t stream) {
+  BnBwdFunctor f{da, x, mean, invstd, scale, shift, relu, C};
+  return run_channel_reduce_fused<2>(f, P, C, 1.f, sums, nullptr, workspace, ws_bytes, counter, stream);
+}
+
+int bn_stats_fused(const float* x, int64_t P, int C, const float* gamma, const float* beta, float eps, float momentum,
+                   float* rmean, float* rvar, float* mean, float* var, float* scale, float* shift, float* invstd,
+                   void* workspace, size_t ws_bytes, unsigned int* counter, cudaStream_t stream) {
+  (void)counter;   // see run_channel_reduce_fused: two launches (partial + final/finalize) instead of three
+  FPD_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "bn_stats_fused: C=%d must be a multiple of 4 in [4,1024]", C);
+  FPD_REQUIRE(P > 0 && mean && var && scale && shift, "bn_stats_fused: bad argument");
+  FPD_REQUIRE((rmean == nullptr) == (rvar == nullptr), "bn_stats_fused: running stats come in pairs");
+  RedGeom g = red_geom(P, C);
+  FPD_REQUIRE(ws_bytes >= (size_t)g.nblocks * C * 2 * sizeof(double), "bn_stats_fused: workspace too small");
+  const size_t smem = ((size_t)g.R * C * 2 + g.R) * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(bn_stats_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        160 * 1024));
+    attr = true;
+  }
+  bn_stats_partial_kernel<<<g.nblocks, kRedThreads, smem, stream>>>(x, P, C, g.L, g.R, g.rows_per_block,
+                                                                    (double*)workspace);
+  FPD_LAUNCH_CHECK();
+  BnFinalize fz{gamma, beta, eps, momentum, mean, var, scale, shift, invstd, rmean, rvar};
+  const int warps = (C + 3) / 4;
+  bn_stats_final_finalize_kernel<<<(warps * 32 + 127) / 128, 128, 0, stream>>>((const double*)workspace, g.nblocks,
+                                                                          g.rows_per_block, P, C, fz);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
 }
 
 int bn_bwd_reduce(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,

@@ -126,6 +126,18 @@ int weight_prep(const float* w_oihw, float* w_hi, float* w_lo, int O, int I, int
 int weight_prep_f16(const float* w_oihw, void* w_hi, void* w_lo, int O, int I, int k, int for_dgrad,
                     cudaStream_t stream);
 
+// Leaner forms of the reductions above (see include/fpd_b200.h): BN statistics second stage + finalize in one kernel,
+// channel sum with the optional 3xFP16 operand scale amax_scale = {S, 1/S}. `counter` is reserved (ignored).
+int channel_sum_fused(const float* dy, int64_t P, int C, float scale, float* out, float* amax_scale, void* workspace,
+                      size_t ws_bytes, unsigned int* counter, cudaStream_t stream);
+int bn_bwd_reduce_fused(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
+                        const float* shift, int relu, int64_t P, int C, float* sums, void* workspace, size_t ws_bytes,
+                        unsigned int* counter, cudaStream_t stream);
+// batch statistics + BatchNorm finalize (affine for the consumers, running-stat update) in one launch
+int bn_stats_fused(const float* x, int64_t P, int C, const float* gamma, const float* beta, float eps, float momentum,
+                   float* rmean, float* rvar, float* mean, float* var, float* scale, float* shift, float* invstd,
+                   void* workspace, size_t ws_bytes, unsigned int* counter, cudaStream_t stream);
+
 // ---- loss.cu : fused FPD loss + gradient ----
 // out_s: S pointers to NHWC [B,h,w,J] student heat-maps; target NCHW [B,J,h,w]; teacher NHWC [B,h,w,J] or null;
 // tw [B,J]; losses[3] = {pose, kd, total}; grads: S pointers (NHWC) or null.

@@ -195,15 +195,22 @@ class Engine:
         b = self.bns[bn_name]
         m = b.mod
         if ctx.training:
-            if x.stats is None:
-                x.stats = ops.bn_stats(x.data)
-            mean, var = x.stats
             count = x.data.numel() // x.data.shape[-1]
             momentum = m.momentum if m.momentum is not None else 0.1
             track = m.track_running_stats and m.running_mean is not None
-            scale, shift, invstd = ops.bn_finalize(mean, var, m.weight.detach(), m.bias.detach(), m.eps, count,
-                                                   m.running_mean if track else None,
-                                                   m.running_var if track else None, momentum)
+            if x.stats is None and ops.FUSED_REDUCE and x.data.shape[-1] % 4 == 0:
+                # statistics + this BN's finalize in one launch
+                mean, var, scale, shift, invstd = ops.bn_stats_finalize(
+                    x.data, m.weight.detach(), m.bias.detach(), m.eps, m.running_mean if track else None,
+                    m.running_var if track else None, momentum)
+                x.stats = (mean, var)
+            else:
+                if x.stats is None:
+                    x.stats = ops.bn_stats(x.data)
+                mean, var = x.stats
+                scale, shift, invstd = ops.bn_finalize(mean, var, m.weight.detach(), m.bias.detach(), m.eps, count,
+                                                       m.running_mean if track else None,
+                                                       m.running_var if track else None, momentum)
             if track and m.num_batches_tracked is not None:
                 ctx.nbt.append(m.num_batches_tracked)
             return scale, shift, mean, invstd, True

@@ -46,6 +46,21 @@ class Workspace:
 
 
 _ws = Workspace()
+_counters = {}
+
+
+def _counter(device):
+    """Zero-initialised ticket counter for the single-launch reductions (one per device and stream; the kernels leave it
+    zero)."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    c = _counters.get(key)
+    if c is None:
+        c = torch.zeros(16, dtype=torch.int32, device=device)
+        _counters[key] = c
+    return c
+
+
+FUSED_REDUCE = os.environ.get("FPD_FUSED_REDUCE", "1") != "0"   # single-launch reductions (A/B switch)
 
 
 def conv2d_tc_supported(cin, cout, k, fused=False):
@@ -265,13 +280,36 @@ def bn_finalize(mean, var, gamma, beta, eps, count, running_mean=None, running_v
     return scale, shift, invstd
 
 
-def channel_sum(dy, scale=1.0):
+def channel_sum(dy, scale=1.0, want_amax=False):
+    """Per-channel sum of dy (bias gradient). want_amax=True also returns the float[2] device tensor {S, 1/S} with S the
+    power of two that puts max|dy| into [2^14, 2^15) (operand scale of the 3xFP16 gradient convolutions), or None when
+    the fused reduction is unavailable (C % 4 != 0)."""
     C = dy.shape[-1]
     P = dy.numel() // C
     out = torch.empty(C, dtype=torch.float32, device=dy.device)
     ws = _ws.get(N.lib().fpd_channel_reduce_workspace_bytes(P, C), dy.device)
+    if FUSED_REDUCE and C % 4 == 0:
+        amax = torch.empty(2, dtype=torch.float32, device=dy.device) if want_amax else None
+        N.check(N.lib().fpd_channel_sum_fused(_p(dy), P, C, float(scale), _p(out), _p(amax), _p(ws), ws.numel(),
+                                              _p(_counter(dy.device)), _stream()), "channel_sum_fused")
+        return (out, amax) if want_amax else out
     N.check(N.lib().fpd_channel_sum(_p(dy), P, C, float(scale), _p(out), _p(ws), ws.numel(), _stream()), "channel_sum")
-    return out
+    return (out, None) if want_amax else out
+
+
+def bn_stats_finalize(x, gamma, beta, eps, running_mean=None, running_var=None, momentum=0.1):
+    """Train-mode BatchNorm2d statistics of x plus the finalize step of one consuming BN, in ONE launch.
+    Returns (mean, var_biased, scale, shift, invstd)."""
+    C = x.shape[-1]
+    P = x.numel() // C
+    mean = torch.empty(C, dtype=torch.float32, device=x.device)
+    var, scale, shift, invstd = (torch.empty_like(mean) for _ in range(4))
+    ws = _ws.get(N.lib().fpd_bn_stats_workspace_bytes(P, C), x.device)
+    N.check(N.lib().fpd_bn_stats_fused(_p(x), P, C, _p(gamma), _p(beta), float(eps), float(momentum),
+                                       _p(running_mean), _p(running_var), _p(mean), _p(var), _p(scale), _p(shift),
+                                       _p(invstd), _p(ws), ws.numel(), _p(_counter(x.device)), _stream()),
+            "bn_stats_fused")
+    return mean, var, scale, shift, invstd
 
 
 def bn_bwd_reduce(da, x, mean, invstd, scale, shift, relu):
@@ -280,6 +318,11 @@ def bn_bwd_reduce(da, x, mean, invstd, scale, shift, relu):
     P = x.numel() // C
     sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
     ws = _ws.get(N.lib().fpd_channel_reduce_workspace_bytes(P, C), x.device)
+    if FUSED_REDUCE:
+        N.check(N.lib().fpd_bn_bwd_reduce_fused(_p(da), _p(x), _p(mean), _p(invstd), _p(scale), _p(shift), int(relu), P,
+                                                C, _p(sums), _p(ws), ws.numel(), _p(_counter(x.device)), _stream()),
+                "bn_bwd_reduce_fused")
+        return sums
     N.check(N.lib().fpd_bn_bwd_reduce(_p(da), _p(x), _p(mean), _p(invstd), _p(scale), _p(shift), int(relu), P, C,
                                       _p(sums), _p(ws), ws.numel(), _stream()), "bn_bwd_reduce")
     return sums

@@ -104,6 +104,24 @@ int fpd_conv2d_tc_h_set_profile_buffer(long long* device_buf);
 int fpd_weight_prep_f16(const float* w_oihw, void* w_hi, void* w_lo, int O, int I, int k, int for_dgrad,
                         fpd_stream_t stream);
 
+/* Leaner forms of fpd_channel_sum / fpd_bn_bwd_reduce / (fpd_bn_stats + fpd_bn_finalize): the BatchNorm statistics'
+ * second stage and the module's finalize (affine + running statistics) run as one kernel (division-free fp64 merge), and
+ * the channel sum can also return the operand scale of the 3xFP16 gradient convolutions: amax_scale (nullable float[2])
+ * receives {S, 1/S} with S the power of two that puts max|dy| into [2^14, 2^15). `counter` is reserved (a single-launch
+ * "last block finishes" variant measured slower on B200 and is disabled); pass a zeroed unsigned int or NULL.
+ * Workspace sizes: fpd_channel_reduce_workspace_bytes / fpd_bn_stats_workspace_bytes.
+ * Replace the per-channel sums of Conv2d bias backward, BatchNorm2d backward and BatchNorm2d train-mode forward
+ * (lib/models/hourglass.py:18-26 modules under loss.backward(), lib/core/function.py:146). */
+int fpd_channel_sum_fused(const float* dy, int64_t P, int C, float scale, float* out, float* amax_scale,
+                          void* workspace, size_t workspace_bytes, unsigned int* counter, fpd_stream_t stream);
+int fpd_bn_bwd_reduce_fused(const float* da, const float* x, const float* mean, const float* invstd,
+                            const float* scale, const float* shift, int relu, int64_t P, int C, float* sums,
+                            void* workspace, size_t workspace_bytes, unsigned int* counter, fpd_stream_t stream);
+int fpd_bn_stats_fused(const float* x, int64_t P, int C, const float* gamma, const float* beta, float eps,
+                       float momentum, float* running_mean, float* running_var, float* mean, float* var_biased,
+                       float* scale, float* shift, float* invstd, void* workspace, size_t workspace_bytes,
+                       unsigned int* counter, fpd_stream_t stream);
+
 /* Tensor-core weight gradient: dw_oihw[Cout,Cin,k,k] = scale * sum_pixels dy (x) a(tap-shifted). */
 int fpd_conv2d_wgrad_tc_supported(int Cin, int Cout, int ksize);
 size_t fpd_conv2d_wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize);

@@ -316,6 +316,48 @@ def test_bn_train_forward_backward(shape):
     assert relerr(dgamma, dg_ref) < 1e-4 and relerr(dbeta, db_ref) < 1e-4
 
 
+@pytest.mark.parametrize("shape", [(4, 64, 64, 128), (32, 4, 4, 64), (3, 16, 12, 48), (2, 128, 128, 32), (2, 8, 8, 16)])
+def test_single_launch_reductions(shape):
+    """Lean reduction forms: channel sum (+ amax scale), BN backward sums, BN statistics + finalize vs torch (repeated)."""
+    o = ops()
+    B, H, W, C = shape
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g) * 3 + 1.5
+    dy = torch.randn(B, H, W, C, device="cuda", generator=g) * 1e-4
+    for rep in range(3):
+        s, amax = o.channel_sum(dy, want_amax=True)
+        torch.cuda.synchronize()
+        ref = dy.double().sum(dim=(0, 1, 2))
+        assert ((s.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+        m = dy.abs().max().item()
+        S, invS = amax.tolist()
+        assert S * invS == 1.0 and 2.0 ** 14 <= m * S < 2.0 ** 15, (m, S)
+    gamma = torch.rand(C, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C, device="cuda", generator=g)
+    rm = torch.zeros(C, device="cuda")
+    rv = torch.ones(C, device="cuda")
+    mean, var, scale, shift, invstd = o.bn_stats_finalize(x, gamma, beta, 1e-5, rm, rv, 0.1)
+    torch.cuda.synchronize()
+    xr = x.double().reshape(-1, C)
+    assert ((mean.double() - xr.mean(0)).abs().max() / xr.mean(0).abs().max()).item() < 1e-6
+    assert ((var.double() - xr.var(0, unbiased=False)).abs().max() / xr.var(0, unbiased=False).max()).item() < 1e-5
+    assert torch.allclose(invstd.double(), 1.0 / torch.sqrt(xr.var(0, unbiased=False) + 1e-5), rtol=1e-5)
+    assert torch.allclose(scale, gamma * invstd) and torch.equal(shift, beta)
+    n = xr.shape[0]
+    assert torch.allclose(rm.double(), 0.1 * xr.mean(0), rtol=1e-5, atol=1e-7)
+    assert torch.allclose(rv.double(), 0.9 + 0.1 * xr.var(0, unbiased=False) * n / (n - 1), rtol=1e-5)
+    # BN backward sums through the fused path equal the two-stage path
+    sums = o.bn_bwd_reduce(dy, x, mean, invstd, scale, shift, True)
+    old = o.FUSED_REDUCE
+    try:
+        o.FUSED_REDUCE = False
+        sums2 = o.bn_bwd_reduce(dy, x, mean, invstd, scale, shift, True)
+    finally:
+        o.FUSED_REDUCE = old
+    torch.cuda.synchronize()
+    assert torch.allclose(sums, sums2, rtol=1e-6, atol=1e-9)   # same fp64 partial scheme, different block geometry
+
+
 def test_split_is_exact_tf32_pair():
     o = ops()
     x = torch.randn(8, 8, 8, 32, device="cuda") * 3
