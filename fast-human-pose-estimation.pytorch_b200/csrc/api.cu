@@ -128,10 +128,10 @@ int fpd_conv2d_tc_h_supported(int Cin, int Cout, int ksize, int H, int W, int f1
 
 int fpd_conv2d_tc_h(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                     int pre_relu, const void* w_hi, const void* w_lo, int f16, const float* bias,
-                    const float* residual, const float* relu_mask, float* y, float out_scale, int B, int H, int W,
-                    int Cin, int Cout, int ksize, fpd_stream_t stream) {
+                    const float* residual, const float* relu_mask, float* y, float out_scale, const float* in_scale,
+                    int B, int H, int W, int Cin, int Cout, int ksize, fpd_stream_t stream) {
   return conv_tc_h_launch(x, pre_mean, pre_scale, pre_shift, pre_relu, w_hi, w_lo, f16, bias, residual, relu_mask, y,
-                          out_scale, B, H, W, Cin, Cout, ksize, device_sm_count(), S(stream));
+                          out_scale, in_scale, B, H, W, Cin, Cout, ksize, device_sm_count(), S(stream));
 }
 
 int fpd_channel_sum_fused(const float* dy, int64_t P, int C, float scale, float* out, float* amax_scale,
@@ -162,11 +162,17 @@ int fpd_weight_prep_f16(const float* w, void* w_hi, void* w_lo, int O, int I, in
   return weight_prep_f16(w, w_hi, w_lo, O, I, k, for_dgrad, S(stream));
 }
 
+int fpd_conv2d_wgrad_tc3_supported(int H, int W, int Cin, int Cout, int ksize) {
+  return wgrad_tc3_supported(H, W, Cin, Cout, ksize) ? 1 : 0;
+}
 int fpd_conv2d_wgrad_tc_supported(int Cin, int Cout, int ksize) {
   return wgrad_tc_supported(Cin, Cout, ksize) ? 1 : 0;
 }
 size_t fpd_conv2d_wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize) {
-  return wgrad_tc_workspace_bytes(B, H, W, Cin, Cout, ksize, device_sm_count());
+  const size_t a = wgrad_tc_workspace_bytes(B, H, W, Cin, Cout, ksize, device_sm_count());
+  const size_t b = wgrad_tc3_supported(H, W, Cin, Cout, ksize)
+                       ? wgrad_tc3_workspace_bytes(B, H, W, Cin, Cout, device_sm_count()) : 0;
+  return a > b ? a : b;
 }
 int fpd_conv2d_wgrad_tc(const float* a_hi, const float* a_lo, const float* dy_hi, const float* dy_lo,
                         float* dw_oihw, float scale, int B, int H, int W, int Cin, int Cout, int ksize,

@@ -69,6 +69,8 @@ struct ConvHParams {
   const float* relu_mask;
   float* y;
   float out_scale;
+  const float* in_scale;   // nullable device float[2] {S, 1/S}: operands are x * S, the epilogue multiplies by 1/S (exact
+                           // powers of two; puts small-magnitude gradients into the fp16 range, see channel_sum amax)
   long long* prof;   // optional per-CTA stall counters [grid][16] (fpd_conv2d_tc_h_set_profile_buffer); null normally
   int dbg;   // timing ablations only (FPD_CONV_DBG bit mask, tools/diag_conv_h.py): 1 no MMA, 2 no weight TMA, 4 no x TMA,
              // 8 no transform/copy work, 16 no epilogue global traffic, 32 no halo split. Results are garbage when set.
@@ -130,7 +132,7 @@ __device__ __forceinline__ void split_f16x2(float v0, float v1, uint32_t& hi, ui
 }
 
 __device__ __forceinline__ float4 affine_relu4(float4 v, uint32_t mean_a, uint32_t scale_a, uint32_t shift_a, int c,
-                                               bool has_affine, int relu) {
+                                               bool has_affine, int relu, float in_s) {
   if (has_affine) {
     const float4 mu = lds128(mean_a + (uint32_t)c * 4u);
     const float4 sc = lds128(scale_a + (uint32_t)c * 4u);
@@ -141,6 +143,7 @@ __device__ __forceinline__ float4 affine_relu4(float4 v, uint32_t mean_a, uint32
   if (relu) {
     v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
   }
+  v.x *= in_s; v.y *= in_s; v.z *= in_s; v.w *= in_s;
   return v;
 }
 
@@ -374,6 +377,7 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int q = warp & 3;
     const uint32_t stg = smem_u32(epi_base) + (uint32_t)q * 4096u;
     const int sub = lane >> 3, ch = lane & 7;
+    const float oscale = p.in_scale ? p.out_scale * __ldg(p.in_scale + 1) : p.out_scale;
     uint32_t tile_iter = 0;
     const bool prof = p.prof != nullptr;
     long long c_tfull = 0;
@@ -436,8 +440,8 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float4 o;
-            o.x = __uint_as_float(v[4 * j + 0]) * p.out_scale; o.y = __uint_as_float(v[4 * j + 1]) * p.out_scale;
-            o.z = __uint_as_float(v[4 * j + 2]) * p.out_scale; o.w = __uint_as_float(v[4 * j + 3]) * p.out_scale;
+            o.x = __uint_as_float(v[4 * j + 0]) * oscale; o.y = __uint_as_float(v[4 * j + 1]) * oscale;
+            o.z = __uint_as_float(v[4 * j + 2]) * oscale; o.w = __uint_as_float(v[4 * j + 3]) * oscale;
             sts128(stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), o);
           }
           if (gw > 16) {
@@ -446,8 +450,8 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float4 o;
-              o.x = __uint_as_float(v[4 * j + 0]) * p.out_scale; o.y = __uint_as_float(v[4 * j + 1]) * p.out_scale;
-              o.z = __uint_as_float(v[4 * j + 2]) * p.out_scale; o.w = __uint_as_float(v[4 * j + 3]) * p.out_scale;
+              o.x = __uint_as_float(v[4 * j + 0]) * oscale; o.y = __uint_as_float(v[4 * j + 1]) * oscale;
+              o.z = __uint_as_float(v[4 * j + 2]) * oscale; o.w = __uint_as_float(v[4 * j + 3]) * oscale;
               sts128(stg + (uint32_t)lane * 128u + (uint32_t)(((j + 4) ^ (lane & 7)) << 4), o);
             }
           }
@@ -492,6 +496,7 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int r = q * 32 + lane;                  // output pixel row of the tile = TMEM lane
     const int dn = r / (p.bw * p.bh), dh_ = (r / p.bw) % p.bh, dw_ = r % p.bw;
     const bool has_affine = p.pre_scale != nullptr;
+    const float in_s = p.in_scale ? __ldg(p.in_scale) : 1.f;
     const uint32_t mean_a = smem_u32(s_mean), scale_a = smem_u32(s_scale), shift_a = smem_u32(s_shift);
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_col0 + (uint32_t)half * 16u;
     int rs = 0, as_ = 0;
@@ -520,7 +525,7 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
               if (box_ok) {
                 v = lds128(xrow + (uint32_t)((i ^ (r & 7)) << 4));
-                v = affine_relu4(v, mean_a, scale_a, shift_a, cb * kCB + half * 32 + i * 4, has_affine, p.pre_relu);
+                v = affine_relu4(v, mean_a, scale_a, shift_a, cb * kCB + half * 32 + i * 4, has_affine, p.pre_relu, in_s);
               }
               split_f16x2(v.x, v.y, hi[2 * i], lo[2 * i]);
               split_f16x2(v.z, v.w, hi[2 * i + 1], lo[2 * i + 1]);
@@ -533,7 +538,7 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
               if (inb && !(p.dbg & 8)) {
                 v = lds128(xrow + (uint32_t)((i ^ (r & 7)) << 4));
-                v = affine_relu4(v, mean_a, scale_a, shift_a, cb * kCB + i * 4, has_affine, p.pre_relu);
+                v = affine_relu4(v, mean_a, scale_a, shift_a, cb * kCB + i * 4, has_affine, p.pre_relu, in_s);
               }
               float4 h, l;
               split_tf32_fast(v.x, h.x, l.x); split_tf32_fast(v.y, h.y, l.y);
@@ -609,8 +614,8 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                   float4 v0 = lds128(xrow + ((c0 ^ sw) << 4));
                   float4 v1 = lds128(xrow + (((c0 + 1) ^ sw) << 4));
                   const int c = cb * kCB + g * 8;
-                  v0 = affine_relu4(v0, mean_a, scale_a, shift_a, c, has_affine, p.pre_relu);
-                  v1 = affine_relu4(v1, mean_a, scale_a, shift_a, c + 4, has_affine, p.pre_relu);
+                  v0 = affine_relu4(v0, mean_a, scale_a, shift_a, c, has_affine, p.pre_relu, in_s);
+                  v1 = affine_relu4(v1, mean_a, scale_a, shift_a, c + 4, has_affine, p.pre_relu, in_s);
                   split_f16x2(v0.x, v0.y, oh.x, ol.x);
                   split_f16x2(v0.z, v0.w, oh.y, ol.y);
                   split_f16x2(v1.x, v1.y, oh.z, ol.z);
@@ -620,7 +625,7 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 if (ok) {
                   const uint32_t xrow = rawst + (uint32_t)pp * 128u;
                   float4 v = lds128(xrow + (((uint32_t)g ^ sw) << 4));
-                  v = affine_relu4(v, mean_a, scale_a, shift_a, cb * kCB + g * 4, has_affine, p.pre_relu);
+                  v = affine_relu4(v, mean_a, scale_a, shift_a, cb * kCB + g * 4, has_affine, p.pre_relu, in_s);
                   float4 h, l;
                   split_tf32_fast(v.x, h.x, l.x); split_tf32_fast(v.y, h.y, l.y);
                   split_tf32_fast(v.z, h.z, l.z); split_tf32_fast(v.w, h.w, l.w);
@@ -775,8 +780,8 @@ bool conv_tc_h_supported(int Cin, int Cout, int ksize, int H, int W, int f16) {
 
 int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                      int pre_relu, const void* w_hi, const void* w_lo, int f16, const float* bias,
-                     const float* residual, const float* relu_mask, float* y, float out_scale, int B, int H, int W,
-                     int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream) {
+                     const float* residual, const float* relu_mask, float* y, float out_scale, const float* in_scale,
+                     int B, int H, int W, int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream) {
   FPD_REQUIRE(x && w_hi && y, "conv_tc_h: null operand");
   FPD_REQUIRE((double)B * H * W * Cout < 4294967296.0, "conv_tc_h: output has 2^32 or more elements");
   FPD_REQUIRE((pre_scale == nullptr) == (pre_shift == nullptr), "conv_tc_h: pre_scale/pre_shift come in pairs");
@@ -792,6 +797,7 @@ int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_sca
     p.dbg = e ? atoi(e) : 0;
   }
   p.prof = g_prof_buf;
+  p.in_scale = in_scale;
   const size_t smem_bytes = (size_t)p.raw_stages * p.raw_stage_bytes + p.split_bytes +
                             (size_t)p.w_stages * p.w_stage_bytes + kEpiBytes + kTailBytes + 1024;
   FPD_REQUIRE(smem_bytes <= 227 * 1024, "conv_tc_h: shared memory plan %zu B too large", smem_bytes);

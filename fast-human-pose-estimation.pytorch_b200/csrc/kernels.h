@@ -41,8 +41,8 @@ bool conv_tc_h_supported(int Cin, int Cout, int ksize, int H, int W, int f16);
 void conv_tc_h_set_profile_buffer(long long* buf);   // per-CTA stall counters [grid][16] (tools/diag_conv_h.py); null = off
 int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                      int pre_relu, const void* w_hi, const void* w_lo, int f16, const float* bias,
-                     const float* residual, const float* relu_mask, float* y, float out_scale, int B, int H, int W,
-                     int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream);
+                     const float* residual, const float* relu_mask, float* y, float out_scale, const float* in_scale,
+                     int B, int H, int W, int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream);
 
 // ---- wgrad_tc.cu : tcgen05 weight-gradient GEMM (K = pixels) ----
 bool wgrad_tc_supported(int Cin, int Cout, int ksize);
@@ -56,6 +56,14 @@ int wgrad_tc_fused_launch(const float* x, const float* pre_mean, const float* pr
                           int pre_relu, const float* dy, int passes, float* dw_oihw, float scale, int B, int H, int W,
                           int Cin, int Cout, int ksize, void* workspace, size_t workspace_bytes, int num_sms,
                           cudaStream_t stream);
+
+// ---- wgrad_tc3.cu : 3x3 weight gradient, one halo tile per pixel block + all taps per CTA (taps = shifted start rows of
+//      the same MN-major shared-memory tile). wgrad_tc_fused_launch dispatches here when the shape is supported. ----
+bool wgrad_tc3_supported(int H, int W, int Cin, int Cout, int ksize);
+size_t wgrad_tc3_workspace_bytes(int B, int H, int W, int Cin, int Cout, int num_sms);
+int wgrad_tc3_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
+                     int pre_relu, const float* dy, int passes, float* dw_oihw, float scale, int B, int H, int W,
+                     int Cin, int Cout, void* workspace, size_t workspace_bytes, int num_sms, cudaStream_t stream);
 
 // ---- conv_simt.cu : generic fp32 CUDA-core convolution (any k / stride / pad, NHWC activations,
 //      OIHW weights). Used for the shapes the tensor-core kernels do not take (7x7 stem, 16-channel

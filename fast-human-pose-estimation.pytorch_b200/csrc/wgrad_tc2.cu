@@ -28,6 +28,8 @@
 // (tcgen05.mma kind::tf32, both operands MN-major), stores an fp32 partial, and a second kernel reduces the
 // partials in a fixed order (deterministic) straight into the OIHW gradient tensor.
 // 3xTF32 (hi/lo operand pairs) keeps fp32-grade accuracy, as in conv_tc.cu.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -55,6 +57,7 @@ struct WgradParams {
   const float* pre_scale;
   const float* pre_shift;
   int pre_relu;
+  int dbg;   // timing ablations (FPD_WGRAD_DBG bit mask): 1 no MMA, 8 no transform work, 2 no TMA. Garbage results when set.
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -72,6 +75,9 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
                       const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // experiment (FPD_WGRAD_DBG & 16/32/64): every operand tile starts 1/2/3 rows (128 B each) off the swizzle-atom
+  // boundary -- do the TMA write pattern and the UMMA read pattern stay consistent (both keyed on absolute address bits)?
+  smem += ((p.dbg >> 4) & 3) * 128;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
   uint64_t* ready_bar = full_bar + p.stages;
   uint64_t* empty_bar = ready_bar + p.stages;
@@ -132,6 +138,7 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
         const int tw = kt % p.tiles_w, th = (kt / p.tiles_w) % p.tiles_h, tn = kt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
         uint8_t* st = smem + (size_t)s * p.stage_bytes;
+        if (p.dbg & 2) { mbar_arrive(&full_bar[s]); __syncwarp(); continue; }
         mbar_expect_tx(&full_bar[s], (uint32_t)half_bytes);   // raw operands only; the lo halves are produced on chip
         for (int j = 0; j < 4; ++j) {
           uint8_t* dst = st + j * kBoxBytes;
@@ -167,6 +174,7 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
         const uint32_t n_lo = m_lo + 4 * kBoxBytes;
 #pragma unroll
         for (int ks = 0; ks < kKp / 8; ++ks) {
+          if (p.dbg & 1) break;
           const uint32_t koff = ks * 1024;  // 8 pixels = two 4-row (512 B) swizzle atoms; SBO = 512 steps between them
           const uint64_t dm_hi = umma_desc_sw128_32b(m_hi + koff, kBoxBytes, 512);
           const uint64_t dn_hi = umma_desc_sw128_32b(n_hi + koff, kBoxBytes, 512);
@@ -229,11 +237,23 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
       const int pn = tn * p.bn + dn, hh0 = th * p.bh + dh_, ww0 = tw * p.bw + dw_;
       mbar_wait(&full_bar[s], ph);
       const uint32_t base = smem_u32(smem + (size_t)s * p.stage_bytes);
-      for (int j = 0; j < 4 + p.nblk_n; ++j) {
-        const uint32_t addr = base + (uint32_t)j * kBoxBytes + row_off;
-        const bool is_act = (j < 4) ? !p.mode_b : (p.mode_b != 0);
-        float4 v = lds128(addr);
-        if (is_act) {
+      // three boxes per round: issue the raw (and parameter) loads of all three before the dependent arithmetic and
+      // stores, so a stage costs ~2 load round trips instead of one per box (the serial form was the largest single
+      // cost of this kernel: tools/diag_wgrad.py, 120 of 287 us on 3x3 64->64 @64x64)
+      const int nbox = (p.dbg & 8) ? 0 : 4 + p.nblk_n;
+      for (int j0 = 0; j0 < nbox; j0 += 3) {
+        float4 v[3], mu[3], sc[3], sh[3];
+        bool act[3], inb[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int j = j0 + u;
+          act[u] = false; inb[u] = true;
+          if (j >= nbox) continue;
+          const uint32_t addr = base + (uint32_t)j * kBoxBytes + row_off;
+          v[u] = lds128(addr);
+          const bool is_act = (j < 4) ? !p.mode_b : (p.mode_b != 0);
+          if (!is_act) continue;
+          act[u] = true;
           int cb, hh = hh0, ww = ww0;
           if (j < 4) {   // mode A, M side: (tap, channel block)
             int tap = g * p.G + j / cblks;
@@ -244,27 +264,38 @@ wgrad_tc_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
             cb = j - 4;
           }
           const int c = cb * 32 + lc * 4;
-          const bool inb = pn < p.B && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W && c < p.Cin;
-          if (inb) {
-            if (has_affine) {
-              const float4 mu = lds128(smem_u32(s_mean) + (uint32_t)c * 4u);
-              const float4 sc = lds128(smem_u32(s_scale) + (uint32_t)c * 4u);
-              const float4 sh = lds128(smem_u32(s_shift) + (uint32_t)c * 4u);
-              v.x = fmaf(v.x - mu.x, sc.x, sh.x); v.y = fmaf(v.y - mu.y, sc.y, sh.y);
-              v.z = fmaf(v.z - mu.z, sc.z, sh.z); v.w = fmaf(v.w - mu.w, sc.w, sh.w);
-            }
-            if (p.pre_relu) {
-              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-            }
-          } else {
-            v = make_float4(0.f, 0.f, 0.f, 0.f);
+          inb[u] = pn < p.B && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W && c < p.Cin;
+          if (inb[u] && has_affine) {
+            mu[u] = lds128(smem_u32(s_mean) + (uint32_t)c * 4u);
+            sc[u] = lds128(smem_u32(s_scale) + (uint32_t)c * 4u);
+            sh[u] = lds128(smem_u32(s_shift) + (uint32_t)c * 4u);
           }
         }
-        float4 h, l;
-        split_tf32_fast(v.x, h.x, l.x); split_tf32_fast(v.y, h.y, l.y);
-        split_tf32_fast(v.z, h.z, l.z); split_tf32_fast(v.w, h.w, l.w);
-        sts128(addr, h);
-        if (split) sts128(addr + (uint32_t)half_bytes, l);
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int j = j0 + u;
+          if (j >= nbox) continue;
+          const uint32_t addr = base + (uint32_t)j * kBoxBytes + row_off;
+          float4 x4 = v[u];
+          if (act[u]) {
+            if (inb[u]) {
+              if (has_affine) {
+                x4.x = fmaf(x4.x - mu[u].x, sc[u].x, sh[u].x); x4.y = fmaf(x4.y - mu[u].y, sc[u].y, sh[u].y);
+                x4.z = fmaf(x4.z - mu[u].z, sc[u].z, sh[u].z); x4.w = fmaf(x4.w - mu[u].w, sc[u].w, sh[u].w);
+              }
+              if (p.pre_relu) {
+                x4.x = fmaxf(x4.x, 0.f); x4.y = fmaxf(x4.y, 0.f); x4.z = fmaxf(x4.z, 0.f); x4.w = fmaxf(x4.w, 0.f);
+              }
+            } else {
+              x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          float4 h, l;
+          split_tf32_fast(x4.x, h.x, l.x); split_tf32_fast(x4.y, h.y, l.y);
+          split_tf32_fast(x4.z, h.z, l.z); split_tf32_fast(x4.w, h.w, l.w);
+          sts128(addr, h);
+          if (split) sts128(addr + (uint32_t)half_bytes, l);
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();                       // one arrival per warp: 256 per-thread arrivals on one barrier serialise
@@ -348,6 +379,9 @@ int wgrad_tc_fused_launch(const float* x, const float* pre_mean, const float* pr
                           int pre_relu, const float* dy, int passes, float* dw_oihw, float scale, int B, int H, int W,
                           int Cin, int Cout, int ksize, void* workspace, size_t workspace_bytes, int num_sms,
                           cudaStream_t stream) {
+  if (wgrad_tc3_supported(H, W, Cin, Cout, ksize))   // 3x3: halo-tile kernel (csrc/wgrad_tc3.cu)
+    return wgrad_tc3_launch(x, pre_mean, pre_scale, pre_shift, pre_relu, dy, passes, dw_oihw, scale, B, H, W, Cin, Cout,
+                            workspace, workspace_bytes, num_sms, stream);
   const float* a_hi = x;
   const float* dy_hi = dy;
   Plan pl = make_plan(Cin, Cout, ksize);
@@ -360,6 +394,10 @@ int wgrad_tc_fused_launch(const float* x, const float* pre_mean, const float* pr
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = ksize * ksize;
   p.passes = passes;
   p.pre_mean = pre_mean; p.pre_scale = pre_scale; p.pre_shift = pre_shift; p.pre_relu = pre_relu;
+  {
+    const char* e = getenv("FPD_WGRAD_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   p.mode_b = pl.mode_b; p.G = pl.G; p.groups = pl.groups; p.N = pl.N; p.nblk_n = pl.N / 32;
   p.bw = pow2_div(W, kKp);
   p.bh = pow2_div(H, kKp / p.bw);
@@ -400,7 +438,7 @@ int wgrad_tc_fused_launch(const float* x, const float* pre_mean, const float* pr
     FPD_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 1024 + tail_bytes;
+  const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 1024 + tail_bytes + 512;
   wgrad_tc_fused_kernel<<<p.groups * p.splits, kThreads, smem_bytes, stream>>>(tm_a_hi, tm_g_hi, p);
   FPD_LAUNCH_CHECK();
   const int64_t total = (int64_t)Cout * Cin * p.taps;

@@ -140,11 +140,17 @@ class PreparedWeights:
         self._fwd[c.name] = e
         return e
 
-    def dgrad(self, c, H, W):
+    def dgrad(self, c, H, W, f16_ok=False):
+        """f16_ok: the caller has the power-of-two operand scale of dY (ops.channel_sum(..., want_amax=True))."""
         e = self._dgrad.get(c.name)
         if e is None:
-            hi, lo = ops.weight_prep(c.weight.detach(), for_dgrad=True, split=self.split)
-            e = (hi, lo, FUSED_DGRAD and ops.conv2d_tc_h_supported(c.cout, c.cin, c.k, H, W, False))
+            if (f16_ok and FUSED_DGRAD and self.split and ops.CONV_F16_DGRAD
+                    and ops.conv2d_tc_h_supported(c.cout, c.cin, c.k, H, W, True)):
+                hi, lo = ops.weight_prep_f16(c.weight.detach(), for_dgrad=True, split=True)
+                e = (hi, lo, True)
+            else:
+                hi, lo = ops.weight_prep(c.weight.detach(), for_dgrad=True, split=self.split)
+                e = (hi, lo, FUSED_DGRAD and ops.conv2d_tc_h_supported(c.cout, c.cin, c.k, H, W, False))
             self._dgrad[c.name] = e
         return e
 
@@ -305,8 +311,10 @@ class Engine:
                     return
                 if residual is not None:
                     residual.add_grad(dy, owned=False)
+                dy_scale = None
                 if c.bias is not None:
-                    ctx.pgrads[c.bias] = ops.channel_sum(dy)
+                    # bias gradient; the same pass over dY yields the power-of-two scale of the 3xFP16 data gradient
+                    ctx.pgrads[c.bias], dy_scale = ops.channel_sum(dy, want_amax=True)
                 dy_hi = dy_lo = None
                 if (c.tc_wgrad and not FUSED_WGRAD) or (need_dx and c.tc_dgrad and not FUSED_DGRAD):
                     dy_hi, dy_lo = ops.affine_act_split(dy, split=split)
@@ -338,9 +346,13 @@ class Engine:
                     return
                 # ---- data gradient w.r.t. the conv input a = act(bn(x))
                 if c.tc_dgrad:
-                    wd_hi, wd_lo, use_h = ctx.weights.dgrad(c, dy.shape[1], dy.shape[2])
+                    wd_hi, wd_lo, use_h = ctx.weights.dgrad(c, dy.shape[1], dy.shape[2], f16_ok=dy_scale is not None)
                     if FUSED_DGRAD:
-                        da = (ops.conv2d_tc_h if use_h else ops.conv2d_tc_fused)(dy, wd_hi, wd_lo, c.k)
+                        if use_h:
+                            da = ops.conv2d_tc_h(dy, wd_hi, wd_lo, c.k,
+                                                 in_scale=dy_scale if wd_hi.dtype == torch.float16 else None)
+                        else:
+                            da = ops.conv2d_tc_fused(dy, wd_hi, wd_lo, c.k)
                     else:
                         da = ops.conv2d_tc(dy_hi, dy_lo, wd_hi, wd_lo, c.k)
                 else:

@@ -167,6 +167,7 @@ def conv2d_tc_fused(x, w_hi, w_lo, ksize, mean=None, scale=None, shift=None, rel
 
 CONV_H = os.environ.get("FPD_CONV_H", "1") != "0"          # generation-5 kernel (halo reuse) where it supports the shape
 CONV_F16 = os.environ.get("FPD_CONV_F16", "1") != "0"      # 3xFP16 operands for the forward convolutions
+CONV_F16_DGRAD = os.environ.get("FPD_CONV_F16_DGRAD", "1") != "0"   # ... and for the data-gradient convolutions (dY * 2^k)
 
 
 def conv2d_tc_h_supported(cin, cout, k, H, W, f16):
@@ -186,7 +187,7 @@ def weight_prep_f16(w_oihw, for_dgrad=False, split=True):
 
 
 def conv2d_tc_h(x, w_hi, w_lo, ksize, mean=None, scale=None, shift=None, relu=False, bias=None, residual=None,
-                relu_mask=None, out=None, out_scale=1.0):
+                relu_mask=None, out=None, out_scale=1.0, in_scale=None):
     """y = conv(relu?((x-mean)*scale+shift)) on the generation-5 kernel (csrc/conv_tc5.cu). The operand precision
     follows the weight dtype: float16 hi/lo -> 3xFP16 (kind::f16), float32 containers -> 3xTF32."""
     B, H, W, Cin = x.shape
@@ -194,8 +195,8 @@ def conv2d_tc_h(x, w_hi, w_lo, ksize, mean=None, scale=None, shift=None, relu=Fa
     f16 = w_hi.dtype == torch.float16
     y = out if out is not None else torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
     N.check(N.lib().fpd_conv2d_tc_h(_p(x), _p(mean), _p(scale), _p(shift), int(relu), _p(w_hi), _p(w_lo), int(f16),
-                                    _p(bias), _p(residual), _p(relu_mask), _p(y), float(out_scale), B, H, W, Cin, Cout,
-                                    ksize, _stream()), "conv2d_tc_h")
+                                    _p(bias), _p(residual), _p(relu_mask), _p(y), float(out_scale), _p(in_scale), B, H,
+                                    W, Cin, Cout, ksize, _stream()), "conv2d_tc_h")
     return y
 
 

@@ -89,12 +89,15 @@ int fpd_conv2d_tc_g(const float* x, const float* pre_mean, const float* pre_scal
  * fetched with its halo and transformed once per channel block, the nine taps are shifted on-chip copies into tensor
  * memory. f16 = 1 selects 3xFP16 operands (x = hi + lo in fp16, tcgen05.mma kind::f16, fp32 accumulate): w_hi / w_lo
  * are then the __half arrays of fpd_weight_prep_f16; f16 = 0: fp32 containers of fpd_weight_prep (3xTF32).
- * w_lo NULL => single pass. Replaces nn.Conv2d after BatchNorm2d + ReLU, lib/models/hourglass.py:34-44. */
+ * w_lo NULL => single pass. in_scale (nullable, device float[2] {S, 1/S}, e.g. from fpd_channel_sum_fused): the operand
+ * is x * S and the result is multiplied by 1/S -- exact powers of two that bring small-magnitude gradients into the fp16
+ * range for the data-gradient convolution. Replaces nn.Conv2d after BatchNorm2d + ReLU (and its data gradient),
+ * lib/models/hourglass.py:34-44. */
 int fpd_conv2d_tc_h_supported(int Cin, int Cout, int ksize, int H, int W, int f16);
 int fpd_conv2d_tc_h(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                     int pre_relu, const void* w_hi, const void* w_lo, int f16, const float* bias,
-                    const float* residual, const float* relu_mask, float* y, float out_scale, int B, int H, int W,
-                    int Cin, int Cout, int ksize, fpd_stream_t stream);
+                    const float* residual, const float* relu_mask, float* y, float out_scale, const float* in_scale,
+                    int B, int H, int W, int Cin, int Cout, int ksize, fpd_stream_t stream);
 /* Profiling aid: when device_buf is non-NULL every following fpd_conv2d_tc_h launch writes, per CTA, 16 int64 stall
  * counters (cycles each warp role spent waiting on each pipeline barrier) to device_buf[blockIdx.x * 16 ...]; NULL
  * switches it off (the default). Not thread-safe; intended for tools/diag_conv_h.py only. */
@@ -136,6 +139,10 @@ int fpd_conv2d_wgrad_tc_fused(const float* x, const float* pre_mean, const float
                               int pre_relu, const float* dy, int passes, float* dw_oihw, float scale, int B, int H,
                               int W, int Cin, int Cout, int ksize, void* workspace, size_t workspace_bytes,
                               fpd_stream_t stream);
+
+/* 1 if fpd_conv2d_wgrad_tc_fused runs this 3x3 shape on the halo-tile kernel (csrc/wgrad_tc3.cu): x fetched once per
+ * pixel block with its halo, taps = shifted start rows of the same shared-memory tile, all taps accumulated per CTA. */
+int fpd_conv2d_wgrad_tc3_supported(int H, int W, int Cin, int Cout, int ksize);
 
 /* Generic fp32 CUDA-core convolution (any k/stride/pad): x NHWC [B,H,W,Cin], w OIHW. */
 int fpd_conv2d_simt_fwd(const float* x, const float* w_oihw, const float* bias, const float* residual, float* y,

@@ -172,6 +172,24 @@ def test_conv2d_tc_h_f16_small_and_large_magnitudes():
         assert relerr(nchw(y), ref) < (2e-4 if mag < 0.1 else 2e-5), "mag %g: %.3e" % (mag, relerr(nchw(y), ref))
 
 
+@pytest.mark.parametrize("mag", [1e-7, 3e-5, 1.0, 1e4])
+def test_conv2d_tc_h_f16_dgrad_with_amax_scale(mag):
+    """3xFP16 data gradient: dY of any magnitude is brought into the fp16 range by the power-of-two scale that the bias-
+    gradient reduction returns (max|dY| * S in [2^14, 2^15)); a wide in-tensor dynamic range must not hurt either."""
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    dy = torch.randn(2, 32, 32, 64, device="cuda", generator=g) * mag
+    dy[0, :4] *= 1e-4    # a region four orders of magnitude below the maximum
+    w = torch.randn(64, 64, 3, 3, device="cuda", generator=g) * (1.0 / 24.0)
+    ref = torch.nn.grad.conv2d_input((2, 64, 32, 32), w, nchw(dy), padding=1)
+    bias_grad, scale = o.channel_sum(dy, want_amax=True)
+    w_hi, w_lo = o.weight_prep_f16(w, for_dgrad=True)
+    da = o.conv2d_tc_h(dy, w_hi, w_lo, 3, in_scale=scale)
+    torch.cuda.synchronize()
+    assert relerr(nchw(da), ref) < 2e-5, "mag %g: %.3e" % (mag, relerr(nchw(da), ref))
+    assert relerr(bias_grad, nchw(dy).sum(dim=(0, 2, 3))) < 1e-5
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 64, 64, 64, 3), (2, 32, 32, 128, 64, 1), (4, 8, 8, 64, 128, 1)])
 def test_conv2d_tc_dgrad_with_relu_mask(shape):
     B, H, W, Cin, Cout, k = shape
@@ -356,6 +374,29 @@ def test_single_launch_reductions(shape):
         o.FUSED_REDUCE = old
     torch.cuda.synchronize()
     assert torch.allclose(sums, sums2, rtol=1e-6, atol=1e-9)   # same fp64 partial scheme, different block geometry
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64, 64), (2, 64, 64, 64, 64), (3, 16, 16, 64, 64), (4, 8, 8, 64, 64),
+                                   (2, 64, 48, 64, 32), (2, 32, 32, 128, 128), (2, 16, 16, 128, 64), (2, 32, 24, 64, 96)])
+@pytest.mark.parametrize("passes", [3, 1])
+def test_conv2d_wgrad_tc3_halo_kernel(shape, passes):
+    """3x3 weight gradient on the halo-tile kernel (csrc/wgrad_tc3.cu: taps = shifted start rows of one shared-memory
+    tile, M = 64 accumulators) vs torch fp32, with the BN-apply + ReLU pre-op fused in."""
+    B, H, W, Cin, Cout = shape
+    o = ops()
+    if not o.N.lib().fpd_conv2d_wgrad_tc3_supported(H, W, Cin, Cout, 3):
+        pytest.skip("shape not taken by wgrad_tc3 (one pipeline stage would not fit): runs on wgrad_tc2")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g) * 2 + 0.3
+    dy = torch.randn(B, Cout, H, W, device="cuda", generator=g)
+    mean = torch.randn(Cin, device="cuda", generator=g)
+    scale = torch.rand(Cin, device="cuda", generator=g) + 0.5
+    shift = torch.randn(Cin, device="cuda", generator=g) * 0.5
+    a = F.relu((x - mean.view(1, -1, 1, 1)) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    ref = torch.nn.grad.conv2d_weight(a, (Cout, Cin, 3, 3), dy, padding=1)
+    dw = o.conv2d_wgrad_tc_fused(nhwc(x), nhwc(dy), 3, mean=mean, scale=scale, shift=shift, relu=True, passes=passes)
+    torch.cuda.synchronize()
+    assert relerr(dw, ref) < (2e-5 if passes == 3 else 3e-3), "wgrad_tc3 %s passes=%d: %.3e" % (shape, passes, relerr(dw, ref))
 
 
 def test_split_is_exact_tf32_pair():
