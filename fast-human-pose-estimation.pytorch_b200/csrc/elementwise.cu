@@ -194,27 +194,41 @@ struct BnFinalize {
 // bn_stats_partial_kernel, in fp64 and a fixed order (deterministic; no division inside the loops, unlike the sequential
 // Chan merge of bn_stats_final_kernel whose fp64 divide chain cost ~7 us per launch). One warp per 4 channels.
 // Reference semantics: nn.BatchNorm2d in train mode incl. the running-statistics update (lib/models/hourglass.py:18-26).
-__global__ void bn_stats_final_finalize_kernel(const double* __restrict__ part, int nblocks, int64_t rows_per_block,
-                                               int64_t P, int C, BnFinalize fz) {
-  const int lane = threadIdx.x & 31;
-  const int c0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4;
-  if (c0 >= C) return;
-  double sw[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-  for (int b = lane; b < nblocks; b += 32) {
+__global__ void __launch_bounds__(256)
+bn_stats_final_finalize_kernel(const double* __restrict__ part, int nblocks, int64_t rows_per_block, int64_t P, int C,
+                               BnFinalize fz) {
+  // one 256-thread block per 4 channels: every thread takes <= ceil(nblocks/256) partial blocks, so each of the two
+  // passes costs about one load round trip + a block reduction (the one-warp-per-channel form walked 19 dependent
+  // round trips per pass: 12 us per launch)
+  __shared__ double red[8][4];
+  __shared__ double s_mu[4];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int c0 = blockIdx.x * 4;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int b = tid; b < nblocks; b += 256) {
     int64_t r0 = (int64_t)b * rows_per_block, r1 = r0 + rows_per_block;
     if (r1 > P) r1 = P;
     const double nb = (double)(r1 > r0 ? r1 - r0 : 0);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (c0 + k < C) sw[k] += nb * part[((size_t)b * C + c0 + k) * 2 + 0];
+      if (c0 + k < C) acc[k] += nb * part[((size_t)b * C + c0 + k) * 2 + 0];
   }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double w = warp_sum(acc[k]);
+    if (lane == 0) red[wid][k] = w;
+  }
+  __syncthreads();
+  if (tid < 4) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w][tid];
+    s_mu[tid] = t / (double)P;
+  }
+  __syncthreads();
   double mu[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) mu[k] = warp_sum(sw[k]) / (double)P;
-  double m2[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-  for (int b = lane; b < nblocks; b += 32) {
+  for (int k = 0; k < 4; ++k) { mu[k] = s_mu[k]; acc[k] = 0.0; }
+  for (int b = tid; b < nblocks; b += 256) {
     int64_t r0 = (int64_t)b * rows_per_block, r1 = r0 + rows_per_block;
     if (r1 > P) r1 = P;
     const double nb = (double)(r1 > r0 ? r1 - r0 : 0);
@@ -222,27 +236,32 @@ __global__ void bn_stats_final_finalize_kernel(const double* __restrict__ part, 
     for (int k = 0; k < 4; ++k)
       if (c0 + k < C) {
         const double d = part[((size_t)b * C + c0 + k) * 2 + 0] - mu[k];
-        m2[k] += part[((size_t)b * C + c0 + k) * 2 + 1] + nb * d * d;
+        acc[k] += part[((size_t)b * C + c0 + k) * 2 + 1] + nb * d * d;
       }
   }
+  __syncthreads();   // red[] is reused
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const double m2t = warp_sum(m2[k]);
-    const int c = c0 + k;
-    if (lane == 0 && c < C) {
-      const float m = (float)mu[k], v = (float)(m2t / (double)P);
-      fz.mean[c] = m;
-      fz.var[c] = v;
-      const float invstd = (float)(1.0 / sqrt((double)v + (double)fz.eps));
-      const float g = fz.gamma ? fz.gamma[c] : 1.f, b = fz.beta ? fz.beta[c] : 0.f;
-      fz.scale[c] = g * invstd;
-      fz.shift[c] = b;   // centred form: y = (x - mean) * scale + shift
-      if (fz.invstd) fz.invstd[c] = invstd;
-      if (fz.rmean) {
-        fz.rmean[c] = (1.f - fz.momentum) * fz.rmean[c] + fz.momentum * m;
-        const float unbiased = P > 1 ? v * ((float)P / (float)(P - 1)) : v;
-        fz.rvar[c] = (1.f - fz.momentum) * fz.rvar[c] + fz.momentum * unbiased;
-      }
+    const double w = warp_sum(acc[k]);
+    if (lane == 0) red[wid][k] = w;
+  }
+  __syncthreads();
+  if (tid < 4 && c0 + tid < C) {
+    double m2t = 0.0;
+    for (int w = 0; w < 8; ++w) m2t += red[w][tid];
+    const int c = c0 + tid;
+    const float m = (float)mu[tid], v = (float)(m2t / (double)P);
+    fz.mean[c] = m;
+    fz.var[c] = v;
+    const float invstd = (float)(1.0 / sqrt((double)v + (double)fz.eps));
+    const float g = fz.gamma ? fz.gamma[c] : 1.f, b = fz.beta ? fz.beta[c] : 0.f;
+    fz.scale[c] = g * invstd;
+    fz.shift[c] = b;   // centred form: y = (x - mean) * scale + shift
+    if (fz.invstd) fz.invstd[c] = invstd;
+    if (fz.rmean) {
+      fz.rmean[c] = (1.f - fz.momentum) * fz.rmean[c] + fz.momentum * m;
+      const float unbiased = P > 1 ? v * ((float)P / (float)(P - 1)) : v;
+      fz.rvar[c] = (1.f - fz.momentum) * fz.rvar[c] + fz.momentum * unbiased;
     }
   }
 }
@@ -1015,9 +1034,8 @@ int bn_stats_fused(const float* x, int64_t P, int C, const float* gamma, const f
                                                                     (double*)workspace);
   FPD_LAUNCH_CHECK();
   BnFinalize fz{gamma, beta, eps, momentum, mean, var, scale, shift, invstd, rmean, rvar};
-  const int warps = (C + 3) / 4;
-  bn_stats_final_finalize_kernel<<<(warps * 32 + 127) / 128, 128, 0, stream>>>((const double*)workspace, g.nblocks,
-                                                                          g.rows_per_block, P, C, fz);
+  bn_stats_final_finalize_kernel<<<(C + 3) / 4, 256, 0, stream>>>((const double*)workspace, g.nblocks,
+                                                                  g.rows_per_block, P, C, fz);
   FPD_LAUNCH_CHECK();
   return FPD_OK;
 }

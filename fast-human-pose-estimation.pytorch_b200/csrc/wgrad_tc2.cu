@@ -332,7 +332,7 @@ __global__ void wgrad_reduce2_kernel(const float* __restrict__ partial, float* _
     const size_t stride = (size_t)groups * 128 * N;
     const float* src = partial + ((size_t)g * 128 + m) * N + n;
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += src[(size_t)s * stride];
+    for (int s = 0; s < splits; ++s) acc += src[(size_t)s * stride];   // (unrolling this x8 measured slower: 15.5 vs 12 us)
     dw[i] = acc * scale;
   }
 }

@@ -21,6 +21,8 @@ _FUSED = os.environ.get("FPD_FUSED", "1").lower()
 FUSED_FWD = _FUSED in ("1", "all", "fwd")     # forward convs (student + teacher)
 FUSED_DGRAD = _FUSED in ("1", "all", "bwd", "dgrad")
 FUSED_WGRAD = _FUSED in ("1", "all", "bwd", "wgrad")
+# forward: run each hourglass level's skip branch on a side stream (see Engine.hourglass)
+FORK_UP1 = os.environ.get("FPD_FORK_UP1", "1") != "0"
 
 
 def precision_passes():
@@ -169,6 +171,7 @@ class Engine:
                 self.bns[name] = BNRef(name, m)
         self._eval_cache = None
         self._eval_cache_key = None
+        self._branch_streams = {}
 
     # ------------------------------------------------------------------ parameter preparation
     def _param_version(self):
@@ -402,8 +405,22 @@ class Engine:
         return x
 
     def hourglass(self, ctx, n, x, prefix, nblocks):
-        """Recursive U, reference hourglass.py:80-92."""
-        up1 = self.residual_seq(ctx, x, "%s.%d.0" % (prefix, n - 1), nblocks)
+        """Recursive U, reference hourglass.py:80-92. The skip branch (up1) does not depend on the lower pyramid: with
+        FORK_UP1 it runs on a per-level side stream, so its wide kernels fill the SMs while the low-resolution chain
+        (4..64 CTAs per kernel, latency-bound) proceeds on the main stream; the branches join before the upsample-add."""
+        done = None
+        if FORK_UP1 and x.data.is_cuda:
+            main = torch.cuda.current_stream()
+            bs = self._branch_stream(main, n)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(bs):
+                bs.wait_event(ev)
+                up1 = self.residual_seq(ctx, x, "%s.%d.0" % (prefix, n - 1), nblocks)
+                done = torch.cuda.Event()
+                done.record(bs)
+        else:
+            up1 = self.residual_seq(ctx, x, "%s.%d.0" % (prefix, n - 1), nblocks)
         low1 = self.maxpool(ctx, x)
         low1 = self.residual_seq(ctx, low1, "%s.%d.1" % (prefix, n - 1), nblocks)
         if n > 1:
@@ -411,7 +428,18 @@ class Engine:
         else:
             low2 = self.residual_seq(ctx, low1, "%s.%d.3" % (prefix, n - 1), nblocks)
         low3 = self.residual_seq(ctx, low2, "%s.%d.2" % (prefix, n - 1), nblocks)
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
         return self.upsample_add(ctx, up1, low3)
+
+    def _branch_stream(self, main, level):
+        """One side stream per (calling stream, hourglass level), created once per engine."""
+        key = (main.cuda_stream, level)
+        st = self._branch_streams.get(key)
+        if st is None:
+            st = torch.cuda.Stream()
+            self._branch_streams[key] = st
+        return st
 
     def hourglass_net(self, ctx, img_nchw):
         """HourglassNet.forward, reference hourglass.py:170-192. Returns the per-stack heat-map Vars (NHWC)."""
