@@ -300,20 +300,30 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   }
 }
 
-// dw[co][ci][tap] = scale * sum_splits partial[split][tap][ci][co]   (fixed order: deterministic)
-__global__ void wgrad_reduce3_kernel(const float* __restrict__ partial, float* __restrict__ dw, float scale, int Cin,
-                                    int Cout, int splits) {
+// dw[co][ci][tap] = scale * sum_splits partial[split][tap][ci][co]. Block = 32 consecutive partial elements (coalesced
+// along co) x 8 split groups, fixed-order final sum (deterministic).
+__global__ void __launch_bounds__(256)
+wgrad_reduce3_kernel(const float* __restrict__ partial, float* __restrict__ dw, float scale, int Cin, int Cout,
+                     int splits) {
+  __shared__ float red[8][32];
   const int64_t total = (int64_t)9 * Cin * Cout;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    // i indexes the partial layout [tap][ci][co] (coalesced reads)
-    const int co = (int)(i % Cout);
-    const int ci = (int)((i / Cout) % Cin);
-    const int tap = (int)(i / ((int64_t)Cout * Cin));
-    float acc = 0.f;
-#pragma unroll 8
-    for (int s = 0; s < splits; ++s) acc += __ldg(partial + (size_t)s * total + i);
-    dw[((size_t)co * Cin + ci) * 9 + tap] = acc * scale;
+  const int lane = threadIdx.x & 31, sg = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;   // index into [tap][ci][co]
+  float acc = 0.f;
+  if (i < total) {
+#pragma unroll 4
+    for (int s = sg; s < splits; s += 8) acc += partial[(size_t)s * total + i];
   }
+  red[sg][lane] = acc;
+  __syncthreads();
+  if (sg != 0 || i >= total) return;
+  float t = red[0][lane];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) t += red[k][lane];
+  const int co = (int)(i % Cout);
+  const int ci = (int)((i / Cout) % Cin);
+  const int tap = (int)(i / ((int64_t)Cout * Cin));
+  dw[((size_t)co * Cin + ci) * 9 + tap] = t * scale;
 }
 
 struct Plan3 {
@@ -422,9 +432,7 @@ int wgrad_tc3_launch(const float* x, const float* pre_mean, const float* pre_sca
   wgrad_tc3_kernel<<<p.groups * p.splits, kThreads, smem_bytes, stream>>>(tm_x, tm_g, p);
   FPD_LAUNCH_CHECK();
   const int64_t total = (int64_t)9 * Cin * Cout;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce3_kernel<<<blocks, 256, 0, stream>>>(p.partial, dw_oihw, scale, Cin, Cout, p.splits);
+  wgrad_reduce3_kernel<<<(int)((total + 31) / 32), 256, 0, stream>>>(p.partial, dw_oihw, scale, Cin, Cout, p.splits);
   FPD_LAUNCH_CHECK();
   return FPD_OK;
 }

@@ -35,6 +35,16 @@ def main():
         for _ in range(iters):
             ops.conv2d_tc_fused(x, w_hi, w_lo, k, mean=mean, scale=scale, shift=shift, relu=True, out=y,
                                 impl="ts" if kind == "conv_ts" else "ss")
+    elif kind in ("conv_h_f16", "conv_h_tf32"):
+        prep = ops.weight_prep_f16 if kind == "conv_h_f16" else ops.weight_prep
+        w_hi, w_lo = prep(w)
+        y = torch.empty(B, H, W, Cout, device="cuda")
+        res = torch.randn(B, H, W, Cout, device="cuda", generator=g)
+        bias = torch.randn(Cout, device="cuda", generator=g)
+        mean = torch.zeros(Cin, device="cuda"); scale = torch.ones(Cin, device="cuda"); shift = torch.zeros(Cin, device="cuda")
+        for _ in range(iters):
+            ops.conv2d_tc_h(x, w_hi, w_lo, k, mean=mean, scale=scale, shift=shift, relu=True, out=y, bias=bias,
+                            residual=res if k == 1 else None)
     elif kind == "wgrad_fused":
         dy = torch.randn(B, H, W, Cout, device="cuda", generator=g)
         for _ in range(iters):

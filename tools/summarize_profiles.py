@@ -37,7 +37,7 @@ def launches(tag):
     for r in data:
         if len(r) < len(hdr):
             continue
-        name = re.sub(r"\(.*", "", r[ix["Kernel Name"]]).replace("fpd::<unnamed>::", "")
+        name = re.sub(r"\(CUtensorMap.*|\(float.*|\(fpd::.*|\(double.*|\(int.*", "", r[ix["Kernel Name"]]).replace("fpd::<unnamed>::", "")
         agg[name][0] += 1
         agg[name][1] += float(r[ix["Metric Value"]].replace(",", "")) / 1000.0
     tot = sum(v[1] for v in agg.values())
@@ -77,6 +77,9 @@ if __name__ == "__main__":
     report(tag, "prof_conv_tc_ss", "conv_tc_kernel (SS, pre-split operands), 3x3 128->128 @64x64, B=32, 3xTF32")
     report(tag, "prof_conv_tc_ts", "conv_tc_ts_kernel (fused transform, A in TMEM), 3x3 128->128 @64x64, B=32, 3xTF32")
     report(tag, "prof_wgrad_tc_fused", "wgrad_tc_fused_kernel, 3x3 64->64 @64x64, B=32, 3xTF32")
+    report(tag, "prof_conv_h_3x3", "conv_tc_h_kernel<f16> (halo reuse, 3xFP16, A in TMEM), 3x3 128->128 @64x64, B=32")
+    report(tag, "prof_conv_h_1x1", "conv_tc_h_kernel<f16> (3xFP16, A in TMEM), 1x1 128->256 + bias + residual @64x64, B=32")
+    report(tag, "prof_wgrad_tc3", "wgrad_tc3_kernel (halo tile, taps as shifted start rows), 3x3 64->64 @64x64, B=32, 3xTF32")
     cup = os.path.join(SRC, "step_cupti_%s.txt" % tag)
     if os.path.exists(cup):
         shutil.copy(cup, os.path.join(OUT, "%s_step_cupti.txt" % tag))
