@@ -162,6 +162,11 @@ int fpd_weight_prep_f16(const float* w, void* w_hi, void* w_lo, int O, int I, in
   return weight_prep_f16(w, w_hi, w_lo, O, I, k, for_dgrad, S(stream));
 }
 
+int fpd_weight_prep_f16_both(const float* w, void* f_hi, void* f_lo, void* d_hi, void* d_lo, int O, int I, int k,
+                             fpd_stream_t stream) {
+  return weight_prep_f16_both(w, f_hi, f_lo, d_hi, d_lo, O, I, k, S(stream));
+}
+
 int fpd_conv2d_wgrad_tc3_supported(int H, int W, int Cin, int Cout, int ksize) {
   return wgrad_tc3_supported(H, W, Cin, Cout, ksize) ? 1 : 0;
 }

@@ -705,6 +705,30 @@ __global__ void weight_prep_f16_kernel(const float* __restrict__ w, __half* __re
   }
 }
 
+// Forward AND data-gradient operand forms from one read of the weights (one launch per convolution instead of two):
+// fwd [tap][O][I], dgrad [taps-1-tap][I][O], both as fp16 hi/lo of w * scale.
+__global__ void weight_prep_f16_both_kernel(const float* __restrict__ w, __half* __restrict__ f_hi,
+                                            __half* __restrict__ f_lo, __half* __restrict__ d_hi,
+                                            __half* __restrict__ d_lo, int O, int I, int k, float scale) {
+  const int taps = k * k;
+  const int64_t n = (int64_t)O * I * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // i indexes the forward layout [tap][o][c]
+    const int c = (int)(i % I);
+    const int o = (int)((i / I) % O);
+    const int tap = (int)(i / ((int64_t)I * O));
+    float v = w[((size_t)o * I + c) * taps + tap];
+    v = fminf(fmaxf(v * scale, -65504.f), 65504.f);
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    f_hi[i] = h;
+    f_lo[i] = l;
+    const size_t di = ((size_t)(taps - 1 - tap) * I + c) * O + o;
+    d_hi[di] = h;
+    d_lo[di] = l;
+  }
+}
+
 // ---- HRNet glue (reference lib/models/pose_hrnet.py:256-263 fuse, :41-57 BasicBlock tail) -------------------
 struct FuseTerms {
   const float4* t[4];
@@ -1082,6 +1106,17 @@ int weight_prep_f16(const float* w_oihw, void* w_hi, void* w_lo, int O, int I, i
   const int64_t n = (int64_t)O * I * k * k;
   weight_prep_f16_kernel<<<grid_for(n, 256), 256, 0, stream>>>(w_oihw, (__half*)w_hi, (__half*)w_lo, O, I, k, for_dgrad,
                                                                (float)(1 << kF16WeightScaleLog2));
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int weight_prep_f16_both(const float* w_oihw, void* f_hi, void* f_lo, void* d_hi, void* d_lo, int O, int I, int k,
+                         cudaStream_t stream) {
+  FPD_REQUIRE(w_oihw && f_hi && f_lo && d_hi && d_lo, "weight_prep_f16_both: null operand");
+  const int64_t n = (int64_t)O * I * k * k;
+  weight_prep_f16_both_kernel<<<grid_for(n, 256), 256, 0, stream>>>(w_oihw, (__half*)f_hi, (__half*)f_lo, (__half*)d_hi,
+                                                                    (__half*)d_lo, O, I, k,
+                                                                    (float)(1 << kF16WeightScaleLog2));
   FPD_LAUNCH_CHECK();
   return FPD_OK;
 }

@@ -133,6 +133,9 @@ int weight_prep(const float* w_oihw, float* w_hi, float* w_lo, int O, int I, int
 // same layouts as __half hi/lo of w * 2^kF16WeightScaleLog2 (3xFP16 operands of conv_tc5.cu)
 int weight_prep_f16(const float* w_oihw, void* w_hi, void* w_lo, int O, int I, int k, int for_dgrad,
                     cudaStream_t stream);
+// forward [tap][O][I] and data-gradient [taps-1-tap][I][O] forms in one launch
+int weight_prep_f16_both(const float* w_oihw, void* f_hi, void* f_lo, void* d_hi, void* d_lo, int O, int I, int k,
+                         cudaStream_t stream);
 
 // Leaner forms of the reductions above (see include/fpd_b200.h): BN statistics second stage + finalize in one kernel,
 // channel sum with the optional 3xFP16 operand scale amax_scale = {S, 1/S}. `counter` is reserved (ignored).

@@ -120,8 +120,10 @@ class PreparedWeights:
         self._fwd = {}
         self._dgrad = {}
 
-    def fwd(self, c, H, W):
-        """-> (w_hi, w_lo, use_h): use_h selects ops.conv2d_tc_h (generation-5 kernel) over the TS kernel."""
+    def fwd(self, c, H, W, also_dgrad=False):
+        """-> (w_hi, w_lo, use_h): use_h selects ops.conv2d_tc_h (generation-5 kernel) over the TS kernel.
+        also_dgrad: a backward pass will want the data-gradient form too -- when both are 3xFP16 they come out of one
+        launch (one read of the weights)."""
         e = self._fwd.get(c.name)
         if e is not None:
             return e
@@ -134,7 +136,12 @@ class PreparedWeights:
             w2[:, :c.cin * c.k * c.k, 0, 0] = w.permute(0, 2, 3, 1).reshape(c.cout, -1)
             w, k, cin = w2, 1, kpad
         if FUSED_FWD and self.split and ops.CONV_F16 and ops.conv2d_tc_h_supported(cin, c.cout, k, H, W, True):
-            hi, lo = ops.weight_prep_f16(w, for_dgrad=False, split=True)
+            if (also_dgrad and not kpad and FUSED_DGRAD and ops.CONV_F16_DGRAD and ops.FUSED_REDUCE and c.bias is not None
+                    and c.tc_dgrad and ops.conv2d_tc_h_supported(c.cout, c.cin, c.k, H, W, True)):
+                (hi, lo), (dhi, dlo) = ops.weight_prep_f16_both(w)
+                self._dgrad[c.name] = (dhi, dlo, True)
+            else:
+                hi, lo = ops.weight_prep_f16(w, for_dgrad=False, split=True)
             e = (hi, lo, True)
         else:
             hi, lo = ops.weight_prep(w, for_dgrad=False, split=self.split)
@@ -145,6 +152,8 @@ class PreparedWeights:
     def dgrad(self, c, H, W, f16_ok=False):
         """f16_ok: the caller has the power-of-two operand scale of dY (ops.channel_sum(..., want_amax=True))."""
         e = self._dgrad.get(c.name)
+        if e is not None and e[0].dtype == torch.float16 and not f16_ok:
+            e = None   # prepared together with the forward form, but no operand scale for dY: use the 3xTF32 form
         if e is None:
             if (f16_ok and FUSED_DGRAD and self.split and ops.CONV_F16_DGRAD
                     and ops.conv2d_tc_h_supported(c.cout, c.cin, c.k, H, W, True)):
@@ -270,7 +279,13 @@ class Engine:
         a_hi = a_lo = None
         kpad = c.im2col_kpad if bn_name is None else 0
         if kpad:
-            cols = ops.im2col(x.data, c.k, c.stride, c.pad, kpad)
+            key = (x.data.data_ptr(), tuple(x.data.shape), c.k, c.stride, c.pad, kpad)
+            if ctx.shared_stem is not None and ctx.shared_stem.get("cols_key") == key:
+                cols = ctx.shared_stem["cols"]     # the same image columns another network already built this step
+            else:
+                cols = ops.im2col(x.data, c.k, c.stride, c.pad, kpad)
+                if ctx.shared_stem is not None and "cols_key" not in ctx.shared_stem:
+                    ctx.shared_stem["cols_key"], ctx.shared_stem["cols"] = key, cols
             w_hi, w_lo, use_h = ctx.weights.fwd(c, cols.shape[1], cols.shape[2])
             conv_fn = ops.conv2d_tc_h if use_h else ops.conv2d_tc_fused
             out = Var(conv_fn(cols, w_hi, w_lo, 1, bias=bias, residual=res))
@@ -292,7 +307,8 @@ class Engine:
                 ctx.tape.append(bwd_stem)
             return out
         if c.tc_fwd:
-            w_hi, w_lo, use_h = ctx.weights.fwd(c, x.data.shape[1], x.data.shape[2])
+            w_hi, w_lo, use_h = ctx.weights.fwd(c, x.data.shape[1], x.data.shape[2],
+                                                also_dgrad=ctx.tape is not None and need_dx)
             if FUSED_FWD:
                 # BN-apply + ReLU + operand split happen inside the conv kernel (no separate HBM pass)
                 conv_fn = ops.conv2d_tc_h if use_h else ops.conv2d_tc_fused
@@ -445,7 +461,12 @@ class Engine:
         """HourglassNet.forward, reference hourglass.py:170-192. Returns the per-stack heat-map Vars (NHWC)."""
         net = self.net
         nb = net.num_blocks
-        x = Var(ops.nchw_to_nhwc(img_nchw))
+        if ctx.shared_stem is not None and ctx.shared_stem.get("img") is img_nchw:
+            x = Var(ctx.shared_stem["nhwc"])      # student and teacher see the same batch: one layout conversion
+        else:
+            x = Var(ops.nchw_to_nhwc(img_nchw))
+            if ctx.shared_stem is not None and "img" not in ctx.shared_stem:
+                ctx.shared_stem["img"], ctx.shared_stem["nhwc"] = img_nchw, x.data
         x = self.conv(ctx, x, "conv1", need_dx=False)
         x = self.bn_act(ctx, x, "bn1", relu=True)
         x = self.residual_seq(ctx, x, "layer1", 1)
@@ -465,13 +486,31 @@ class Engine:
                 x = self.conv(ctx, score, "score_.%d" % i, residual=t)
         return outs
 
+    def prepare_stem(self, img_nchw, shared_stem):
+        """Fills shared_stem with the NHWC image and (when the stem conv runs as im2col + tensor-core GEMM) its columns,
+        on the current stream, so that several networks consuming this batch can share them."""
+        if not (img_nchw.is_contiguous() and img_nchw.dtype == torch.float32):
+            return
+        c = self.convs.get("conv1")
+        shared_stem["img"], shared_stem["nhwc"] = img_nchw, ops.nchw_to_nhwc(img_nchw)
+        if c is not None and c.im2col_kpad:
+            kpad = c.im2col_kpad
+            x = shared_stem["nhwc"]
+            shared_stem["cols_key"] = (x.data_ptr(), tuple(x.shape), c.k, c.stride, c.pad, kpad)
+            shared_stem["cols"] = ops.im2col(x, c.k, c.stride, c.pad, kpad)
+
     def run_network(self, ctx, img_nchw):
         """Topology hook: subclasses (engine_hrnet.HRNetEngine) override this."""
         return self.hourglass_net(ctx, img_nchw)
 
     # ------------------------------------------------------------------ entry points
-    def forward(self, img_nchw, training, record_tape):
+    def forward(self, img_nchw, training, record_tape, shared_stem=None):
+        """shared_stem: optional dict shared between the networks that consume the SAME input batch in one step (FPD:
+        student + frozen teacher). The first forward stores the NHWC image and the stem's im2col columns in it, later
+        ones reuse them (the caller orders the streams: the producer's forward must have been enqueued first and the
+        consumer's stream must wait on it)."""
         ctx = _Ctx()
+        ctx.shared_stem = shared_stem
         ctx.training = training
         ctx.passes = precision_passes()
         ctx.tape = [] if record_tape else None
@@ -483,7 +522,8 @@ class Engine:
             if record_tape:
                 w = PreparedWeights(ctx.passes)
             ctx.weights, ctx.affine = w, affine
-        outs = self.run_network(ctx, img_nchw.contiguous().float())
+        img = img_nchw if (img_nchw.is_contiguous() and img_nchw.dtype == torch.float32) else img_nchw.contiguous().float()
+        outs = self.run_network(ctx, img)
         if ctx.nbt:
             torch._foreach_add_(ctx.nbt, 1)
         ctx.outs = outs
@@ -518,3 +558,4 @@ class _Ctx:
         self.outs = None
         self.wgrad_stream = None
         self.keepalive = []
+        self.shared_stem = None

@@ -186,6 +186,19 @@ def weight_prep_f16(w_oihw, for_dgrad=False, split=True):
     return hi, lo
 
 
+def weight_prep_f16_both(w_oihw):
+    """-> ((fwd_hi, fwd_lo), (dgrad_hi, dgrad_lo)) in one launch."""
+    _chk(w_oihw, "w")
+    O, I, k, _ = w_oihw.shape
+    f_hi = torch.empty((k * k, O, I), dtype=torch.float16, device=w_oihw.device)
+    f_lo = torch.empty_like(f_hi)
+    d_hi = torch.empty((k * k, I, O), dtype=torch.float16, device=w_oihw.device)
+    d_lo = torch.empty_like(d_hi)
+    N.check(N.lib().fpd_weight_prep_f16_both(_p(w_oihw), _p(f_hi), _p(f_lo), _p(d_hi), _p(d_lo), O, I, k, _stream()),
+            "weight_prep_f16_both")
+    return (f_hi, f_lo), (d_hi, d_lo)
+
+
 def conv2d_tc_h(x, w_hi, w_lo, ksize, mean=None, scale=None, shift=None, relu=False, bias=None, residual=None,
                 relu_mask=None, out=None, out_scale=1.0, in_scale=None):
     """y = conv(relu?((x-mean)*scale+shift)) on the generation-5 kernel (csrc/conv_tc5.cu). The operand precision

@@ -13,10 +13,14 @@ The teacher is forward-only (its gradients never influence the student update; t
 backward is wasted work). `plain=True` drops the teacher (function.train semantics,
 function.py:44-63).
 """
+import os
+
 import torch
 
 from . import ops
 from . import _native as N
+
+SHARE_STEM = os.environ.get("FPD_SHARE_STEM", "1") != "0"   # student + teacher share the NHWC image and stem im2col
 
 
 class FlatParams:
@@ -121,13 +125,18 @@ class FPDTrainStep:
             # the frozen teacher's forward is independent of the student's: run it on a second stream so its many
             # small-grid kernels (low-resolution hourglass levels) fill SMs the student leaves idle. It uses no shared
             # workspace (eval-mode BN: no statistics passes), so the two streams touch disjoint memory.
+            # Both networks start from the same image: the NHWC conversion and the 7x7-stem im2col columns (335 MB at
+            # B=32) are built once, on the main stream, before the fork.
             main = torch.cuda.current_stream()
+            stem = {} if SHARE_STEM else None
+            if stem is not None:
+                s_eng.prepare_stem(x, stem)
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
-                t_ctx = self.teacher.engine().forward(x, False, record_tape=False)
+                t_ctx = self.teacher.engine().forward(x, False, record_tape=False, shared_stem=stem)
                 self._t_keep = t_ctx            # keep every teacher tensor alive until the streams have joined
                 t_last = t_ctx.outs[-1].data
-            ctx = s_eng.forward(x, True, record_tape=True)
+            ctx = s_eng.forward(x, True, record_tape=True, shared_stem=stem)
             main.wait_stream(self._side)
         else:
             ctx = s_eng.forward(x, True, record_tape=True)

@@ -98,6 +98,10 @@ int fpd_conv2d_tc_h(const float* x, const float* pre_mean, const float* pre_scal
                     int pre_relu, const void* w_hi, const void* w_lo, int f16, const float* bias,
                     const float* residual, const float* relu_mask, float* y, float out_scale, const float* in_scale,
                     int B, int H, int W, int Cin, int Cout, int ksize, fpd_stream_t stream);
+/* Forward ([tap][O][I]) and data-gradient ([taps-1-tap][I][O]) __half hi/lo forms of w * 2^8 from one read of the
+ * weights: one launch per convolution and training step instead of two. */
+int fpd_weight_prep_f16_both(const float* w_oihw, void* f_hi, void* f_lo, void* d_hi, void* d_lo, int O, int I, int k,
+                             fpd_stream_t stream);
 /* Profiling aid: when device_buf is non-NULL every following fpd_conv2d_tc_h launch writes, per CTA, 16 int64 stall
  * counters (cycles each warp role spent waiting on each pipeline barrier) to device_buf[blockIdx.x * 16 ...]; NULL
  * switches it off (the default). Not thread-safe; intended for tools/diag_conv_h.py only. */
