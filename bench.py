@@ -26,7 +26,7 @@ if ROOT not in sys.path:
 
 NS = types.SimpleNamespace
 FLOP_PER_IMAGE = 79.633e9  # student fwd 7.8145 + bwd 15.629 + teacher fwd 56.189 GFLOP
-CONV_H_3X3_DRAM_BYTES = None   # filled from the ncu capture (profiles/); None until measured
+CONV_H_3X3_DRAM_BYTES = 87.09e6   # dram__bytes_read + write of that kernel and shape, profiles/r1c_prof_conv_h_3x3.md
 WORKLOAD = "hourglass FPD train: student s4 f128 + frozen teacher s8 f256, 256x256, batch 32/GPU"
 
 
