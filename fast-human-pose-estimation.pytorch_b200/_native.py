@@ -39,8 +39,6 @@ _SIGNATURES = {
     "fpd_channel_sum_fused": (c_int, [P, c_int64, c_int, c_float, P, P, P, c_size_t, P, P]),
     "fpd_bn_bwd_reduce_fused": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int, P, P, c_size_t, P, P]),
     "fpd_bn_stats_fused": (c_int, [P, c_int64, c_int, P, P, c_float, c_float, P, P, P, P, P, P, P, P, c_size_t, P, P]),
-    "fpd_conv2d_tc_h_dgrad_bnbwd": (c_int, [P, P, P, c_int, P, c_float, P, P, P, P, P, P, c_int, P, P, c_size_t, c_int,
-                                            c_int, c_int, c_int, c_int, c_int, P]),
     "fpd_weight_prep_f16_both": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     "fpd_weight_prep_f16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     "fpd_conv2d_wgrad_tc3_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),

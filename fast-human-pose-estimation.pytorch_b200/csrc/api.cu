@@ -162,16 +162,6 @@ int fpd_weight_prep_f16(const float* w, void* w_hi, void* w_lo, int O, int I, in
   return weight_prep_f16(w, w_hi, w_lo, O, I, k, for_dgrad, S(stream));
 }
 
-int fpd_conv2d_tc_h_dgrad_bnbwd(const float* dy, const void* w_hi, const void* w_lo, int f16, float* da, float out_scale,
-                                const float* in_scale, const float* bn_x, const float* bn_mean, const float* bn_invstd,
-                                const float* bn_scale, const float* bn_shift, int bn_relu, float* sums, void* workspace,
-                                size_t workspace_bytes, int B, int H, int W, int Cin, int Cout, int ksize,
-                                fpd_stream_t stream) {
-  ConvBnBwd b{bn_x, bn_mean, bn_invstd, bn_scale, bn_shift, bn_relu, sums, workspace, workspace_bytes};
-  return conv_tc_h_launch(dy, nullptr, nullptr, nullptr, 0, w_hi, w_lo, f16, nullptr, nullptr, nullptr, da, out_scale,
-                          in_scale, B, H, W, Cin, Cout, ksize, device_sm_count(), S(stream), &b);
-}
-
 int fpd_weight_prep_f16_both(const float* w, void* f_hi, void* f_lo, void* d_hi, void* d_lo, int O, int I, int k,
                              fpd_stream_t stream) {
   return weight_prep_f16_both(w, f_hi, f_lo, d_hi, d_lo, O, I, k, S(stream));

@@ -45,9 +45,7 @@ constexpr int kMaxCinH = 512;
 constexpr int kParamFloats = kMaxCinH + 64;
 constexpr int kMaxRing = 8;
 constexpr int kTailBytes = 1024 + 3 * kParamFloats * 4;
-constexpr int kEpiStage = 4 * 32 * 128;   // epilogue staging: one [32 rows x 128 B] tile per epilogue warp
-constexpr int kBnbChannels = 128;         // fused BN-backward sums: per-warp accumulators [2][128] floats
-constexpr int kBnbBytes = 4 * 2 * kBnbChannels * 4;   // only reserved by launches that use the fused BN-backward sums
+constexpr int kEpiBytes = 4 * 32 * 128;   // epilogue staging: one [32 rows x 128 B] tile per epilogue warp
 
 struct ConvHParams {
   int B, H, W, Cin, Cout;
@@ -64,7 +62,6 @@ struct ConvHParams {
   int split_bytes;         // 0: direct path
   int w_tile_bytes, w_stage_bytes, w_stages;
   int a_stages, a_col0, tmem_cols, acc_stages;
-  int epi_bytes;           // epilogue staging (+ the fused BN-backward accumulators when used)
   const float* pre_mean;
   const float* pre_scale;
   const float* pre_shift;
@@ -76,18 +73,6 @@ struct ConvHParams {
   float out_scale;
   const float* in_scale;   // nullable device float[2] {S, 1/S}: operands are x * S, the epilogue multiplies by 1/S (exact
                            // powers of two; puts small-magnitude gradients into the fp16 range, see channel_sum amax)
-  // Fused BatchNorm-backward reduction (data-gradient launches only; null otherwise): y = da is the gradient w.r.t. the
-  // BN output a = relu?((xb - mean) * scale + shift); the epilogue also accumulates, per output channel,
-  //   S0 = sum dz,  S1 = sum dz * (xb - mean) * invstd,  dz = da masked by the ReLU,
-  // into bnb_partial[blockIdx][2][Cout] (reduced in a fixed order by bnb_final_kernel) -- the separate
-  // channel_reduce_partial pass over (da, xb) and its launch drop out of the backward critical path.
-  const float* bnb_x;       // [B,H,W,Cout] input of that BatchNorm (same shape as y)
-  const float* bnb_mean;
-  const float* bnb_invstd;
-  const float* bnb_scale;
-  const float* bnb_shift;
-  int bnb_relu;
-  float* bnb_partial;
   long long* prof;   // optional per-CTA stall counters [grid][16] (fpd_conv2d_tc_h_set_profile_buffer); null normally
   int dbg;   // timing ablations only (FPD_CONV_DBG bit mask, tools/diag_conv_h.py): 1 no MMA, 2 no weight TMA, 4 no x TMA,
              // 8 no transform/copy work, 16 no epilogue global traffic, 32 no halo split. Results are garbage when set.
@@ -202,7 +187,7 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   uint8_t* split_base = raw_base + (size_t)p.raw_stages * p.raw_stage_bytes;
   uint8_t* w_base = split_base + p.split_bytes;
   uint8_t* epi_base = w_base + (size_t)p.w_stages * p.w_stage_bytes;
-  uint8_t* tail = epi_base + p.epi_bytes;
+  uint8_t* tail = epi_base + kEpiBytes;
   uint64_t* raw_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* raw_empty = raw_full + kMaxRing;
   uint64_t* w_full = raw_empty + kMaxRing;
@@ -410,12 +395,6 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const uint32_t stg = smem_u32(epi_base) + (uint32_t)q * 4096u;
     const int sub = lane >> 3, ch = lane & 7;
     const float oscale = p.in_scale ? p.out_scale * __ldg(p.in_scale + 1) : p.out_scale;
-    float* bnb_acc = reinterpret_cast<float*>(epi_base + kEpiStage) + q * (2 * kBnbChannels);   // this warp's [2][128]
-    const float* aux = p.residual ? p.residual : p.bnb_x;   // the one extra [B,H,W,Cout] input of the epilogue (never both)
-    if (p.bnb_x) {
-      for (int i = lane; i < 2 * kBnbChannels; i += 32) bnb_acc[i] = 0.f;
-      __syncwarp();
-    }
     uint32_t tile_iter = 0;
     const bool prof = p.prof != nullptr;
     long long c_tfull = 0;
@@ -440,7 +419,7 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       // Pull the residual rows towards the L2 one tile ahead (this tile's too, the first time): the loads below then
       // cost an L2 hit instead of an HBM round trip per 32-column group, which was what paced the 1x1 convolutions
       // (epilogue busy 6 us per tile against 3 us of HBM time, tools/diag_conv_h.py --stalls).
-      if (aux && !(p.dbg & 16) && ch == 0) {
+      if (p.residual && !(p.dbg & 16) && ch == 0) {
         for (int which = (tile_iter == 0 ? 0 : 1); which < 2; ++which) {
           const int tl = tile + which * (int)gridDim.x;
           if (tl >= p.num_tiles) break;
@@ -452,7 +431,7 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             if (pn >= p.B) continue;
             const size_t off = (((size_t)pn * p.H + tp.h0 + (m / p.bw) % p.bh) * p.W + tp.w0 + (m % p.bw)) * (size_t)p.Cout +
                                (size_t)tp.n0w;
-            for (int c = 0; c < p.nt; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(aux + off + c));
+            for (int c = 0; c < p.nt; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + off + c));
           }
         }
       }
@@ -466,10 +445,10 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         // residual rows of this group: issued before the TMEM read-out so their latency overlaps it (and kept apart from
         // the stores below -- y and residual may alias as far as the compiler knows, which would serialise load/store pairs)
         float4 r4[8];
-        if (aux && act) {
+        if (p.residual && act) {
 #pragma unroll
           for (int it = 0; it < 8; ++it)
-            if (vmask & (1u << it)) r4[it] = __ldg(reinterpret_cast<const float4*>(aux + (size_t)pixoff[it] + col));
+            if (vmask & (1u << it)) r4[it] = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)pixoff[it] + col));
         }
         {
           uint32_t v[16];
@@ -495,17 +474,9 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           }
         }
         __syncwarp();
-        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};   // fused BN-backward sums of this group
         if (act) {
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + t.n0w + col));
-          float4 pm, pi, ps, ph;   // BatchNorm parameters of this lane's four channels (fused BN-backward sums)
-          if (p.bnb_x) {
-            pm = __ldg(reinterpret_cast<const float4*>(p.bnb_mean + t.n0w + col));
-            pi = __ldg(reinterpret_cast<const float4*>(p.bnb_invstd + t.n0w + col));
-            ps = __ldg(reinterpret_cast<const float4*>(p.bnb_scale + t.n0w + col));
-            ph = __ldg(reinterpret_cast<const float4*>(p.bnb_shift + t.n0w + col));
-          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rl = it * 4 + sub;
@@ -522,38 +493,6 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 o.z = k.z > 0.f ? o.z : 0.f; o.w = k.w > 0.f ? o.w : 0.f;
               }
               *reinterpret_cast<float4*>(p.y + off) = o;
-              if (p.bnb_x) {
-                const float4 xv = r4[it];
-                const float oe[4] = {o.x, o.y, o.z, o.w}, xe[4] = {xv.x, xv.y, xv.z, xv.w};
-                const float me[4] = {pm.x, pm.y, pm.z, pm.w}, ie[4] = {pi.x, pi.y, pi.z, pi.w};
-                const float se[4] = {ps.x, ps.y, ps.z, ps.w}, he[4] = {ph.x, ph.y, ph.z, ph.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float xc = xe[j] - me[j];
-                  const bool on = !p.bnb_relu || (fmaf(xc, se[j], he[j]) > 0.f);
-                  const float dz = on ? oe[j] : 0.f;
-                  s0[j] += dz;
-                  s1[j] = fmaf(dz, xc * ie[j], s1[j]);
-                }
-              }
-            }
-          }
-        }
-        if (p.bnb_x) {
-          // rows of this group: 8 per lane, 4 lanes (sub) per channel chunk -> one owner lane per chunk adds into the
-          // warp's accumulator (fixed order: deterministic). Every lane takes part in the shuffles.
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            s0[j] += __shfl_xor_sync(0xffffffffu, s0[j], 8);
-            s0[j] += __shfl_xor_sync(0xffffffffu, s0[j], 16);
-            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);
-            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
-          }
-          if (act && sub == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              bnb_acc[col + j] += s0[j];
-              bnb_acc[kBnbChannels + col + j] += s1[j];
             }
           }
         }
@@ -561,22 +500,6 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       }
       tc_fence_before_sync();
       warp_arrive(&tmem_empty[acs], lane);
-    }
-    if (p.bnb_x) {
-      // the four epilogue warps' accumulators -> this CTA's partial [2][Cout]
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      const float* acc0 = reinterpret_cast<const float*>(epi_base + kEpiStage);
-      const int e = (warp - 2) * 32 + lane;   // 0..127
-      if (e < p.Cout) {
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          a0 += acc0[w * 2 * kBnbChannels + e];
-          a1 += acc0[w * 2 * kBnbChannels + kBnbChannels + e];
-        }
-        p.bnb_partial[(size_t)blockIdx.x * 2 * p.Cout + e] = a0;
-        p.bnb_partial[(size_t)blockIdx.x * 2 * p.Cout + p.Cout + e] = a1;
-      }
     }
     if (prof && warp == 2 && lane == 0) {
       long long* o = p.prof + (size_t)blockIdx.x * 16;
@@ -793,17 +716,6 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 
 long long* g_prof_buf = nullptr;
 
-// sums[i] = sum over the CTAs' partials [grid][2][C], one warp per output, fixed order, fp64 accumulation
-__global__ void bnb_final_kernel(const float* __restrict__ partial, int nblocks, int n /*2C*/, float* __restrict__ sums) {
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (i >= n) return;
-  double s = 0.0;
-  for (int b = lane; b < nblocks; b += 32) s += (double)partial[(size_t)b * n + i];
-  s = warp_sum(s);
-  if (lane == 0) sums[i] = (float)s;
-}
-
 int pow2_floor_div(int x, int cap) {
   int r = 1;
   while (r * 2 <= cap && x % (r * 2) == 0) r *= 2;
@@ -813,7 +725,7 @@ int pow2_floor_div(int x, int cap) {
 int align1024(int x) { return (x + 1023) / 1024 * 1024; }
 
 // Fills the geometry / ring sizes; returns false if the shape does not fit.
-bool plan(ConvHParams& p, int B, int H, int W, int Cin, int Cout, int ksize, int f16, int passes, bool bnb = false) {
+bool plan(ConvHParams& p, int B, int H, int W, int Cin, int Cout, int ksize, int f16, int passes) {
   const int cbch = f16 ? 64 : 32;
   if (!(ksize == 1 || ksize == 3)) return false;
   if (Cin < 4 || Cin > kMaxCinH || Cin % (f16 ? 8 : 4) != 0) return false;
@@ -847,8 +759,7 @@ bool plan(ConvHParams& p, int B, int H, int W, int Cin, int Cout, int ksize, int
   if (p.a_stages < 2) return false;
   p.w_tile_bytes = nt * 128;
   p.w_stage_bytes = (passes == 3 ? 2 : 1) * p.w_tile_bytes;
-  p.epi_bytes = kEpiStage + (bnb ? kBnbBytes : 0);
-  const int budget = 227 * 1024 - 1024 - kTailBytes - p.epi_bytes;
+  const int budget = 227 * 1024 - 1024 - kTailBytes - kEpiBytes;
   const int boxes = f16 ? 2 : 1;
   if (ksize == 3) {
     p.halo_w = p.bw + 2; p.halo_h = p.bh + 2;
@@ -901,22 +812,13 @@ bool conv_tc_h_supported(int Cin, int Cout, int ksize, int H, int W, int f16) {
 int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                      int pre_relu, const void* w_hi, const void* w_lo, int f16, const float* bias,
                      const float* residual, const float* relu_mask, float* y, float out_scale, const float* in_scale,
-                     int B, int H, int W, int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream,
-                     const ConvBnBwd* bnb) {
+                     int B, int H, int W, int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream) {
   FPD_REQUIRE(x && w_hi && y, "conv_tc_h: null operand");
-  if (bnb) {
-    FPD_REQUIRE(Cout <= kBnbChannels && !residual, "conv_tc_h: fused BN-backward sums need Cout <= %d and no residual",
-                kBnbChannels);
-    FPD_REQUIRE(bnb->x && bnb->mean && bnb->invstd && bnb->scale && bnb->shift && bnb->sums && bnb->workspace,
-                "conv_tc_h: fused BN-backward sums: null argument");
-    FPD_REQUIRE(bnb->workspace_bytes >= (size_t)num_sms * 2 * Cout * sizeof(float),
-                "conv_tc_h: fused BN-backward sums: workspace too small");
-  }
   FPD_REQUIRE((double)B * H * W * Cout < 4294967296.0, "conv_tc_h: output has 2^32 or more elements");
   FPD_REQUIRE((pre_scale == nullptr) == (pre_shift == nullptr), "conv_tc_h: pre_scale/pre_shift come in pairs");
   FPD_REQUIRE(pre_scale != nullptr || pre_mean == nullptr, "conv_tc_h: pre_mean needs pre_scale/pre_shift");
   ConvHParams p{};
-  FPD_REQUIRE(plan(p, B, H, W, Cin, Cout, ksize, f16, w_lo ? 3 : 1, bnb != nullptr),
+  FPD_REQUIRE(plan(p, B, H, W, Cin, Cout, ksize, f16, w_lo ? 3 : 1),
               "conv_tc_h: unsupported shape Cin=%d Cout=%d k=%d H=%d W=%d f16=%d", Cin, Cout, ksize, H, W, f16);
   p.pre_mean = pre_mean; p.pre_scale = pre_scale; p.pre_shift = pre_shift; p.pre_relu = pre_relu;
   p.bias = bias; p.residual = residual; p.relu_mask = relu_mask; p.y = y;
@@ -927,12 +829,8 @@ int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_sca
   }
   p.prof = g_prof_buf;
   p.in_scale = in_scale;
-  if (bnb) {
-    p.bnb_x = bnb->x; p.bnb_mean = bnb->mean; p.bnb_invstd = bnb->invstd; p.bnb_scale = bnb->scale;
-    p.bnb_shift = bnb->shift; p.bnb_relu = bnb->relu; p.bnb_partial = (float*)bnb->workspace;
-  }
   const size_t smem_bytes = (size_t)p.raw_stages * p.raw_stage_bytes + p.split_bytes +
-                            (size_t)p.w_stages * p.w_stage_bytes + p.epi_bytes + kTailBytes + 1024;
+                            (size_t)p.w_stages * p.w_stage_bytes + kEpiBytes + kTailBytes + 1024;
   FPD_REQUIRE(smem_bytes <= 227 * 1024, "conv_tc_h: shared memory plan %zu B too large", smem_bytes);
 
   CUtensorMap tm_x, tm_w_hi, tm_w_lo;
@@ -964,10 +862,6 @@ int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_sca
   if (f16) conv_tc_h_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w_hi, tm_w_lo, p);
   else conv_tc_h_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w_hi, tm_w_lo, p);
   FPD_LAUNCH_CHECK();
-  if (bnb) {
-    bnb_final_kernel<<<(2 * Cout * 32 + 127) / 128, 128, 0, stream>>>(p.bnb_partial, grid, 2 * Cout, bnb->sums);
-    FPD_LAUNCH_CHECK();
-  }
   return FPD_OK;
 }
 

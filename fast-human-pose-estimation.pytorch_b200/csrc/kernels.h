@@ -37,21 +37,12 @@ int conv_tc_g_launch(const float* x, const float* pre_mean, const float* pre_sca
 //      and optional 3xFP16 operands (f16 = 1: w_hi / w_lo are __half [tap][Cout][Cin] from weight_prep_f16, pre-scaled
 //      by 2^kF16WeightScaleLog2; f16 = 0: fp32 containers from weight_prep, 3xTF32) ----
 constexpr int kF16WeightScaleLog2 = 8;
-// optional fused BatchNorm-backward reduction of a data-gradient launch (see ConvHParams::bnb_x)
-struct ConvBnBwd {
-  const float* x; const float* mean; const float* invstd; const float* scale; const float* shift;
-  int relu;
-  float* sums;            // [2*Cout]: sum dz, sum dz*xhat
-  void* workspace;        // >= sm_count * 2 * Cout floats
-  size_t workspace_bytes;
-};
 bool conv_tc_h_supported(int Cin, int Cout, int ksize, int H, int W, int f16);
 void conv_tc_h_set_profile_buffer(long long* buf);   // per-CTA stall counters [grid][16] (tools/diag_conv_h.py); null = off
 int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                      int pre_relu, const void* w_hi, const void* w_lo, int f16, const float* bias,
                      const float* residual, const float* relu_mask, float* y, float out_scale, const float* in_scale,
-                     int B, int H, int W, int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream,
-                     const ConvBnBwd* bnb = nullptr);
+                     int B, int H, int W, int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream);
 
 // ---- wgrad_tc.cu : tcgen05 weight-gradient GEMM (K = pixels) ----
 bool wgrad_tc_supported(int Cin, int Cout, int ksize);

@@ -235,15 +235,14 @@ class Engine:
         scale, shift, rmean, rinvstd = ctx.affine[bn_name]
         return scale, shift, rmean, rinvstd, False
 
-    def _bn_backward(self, ctx, x, bn_name, relu, da, aff, sums=None):
-        """dL/d(act(bn(x))) = da  ->  accumulates dL/dx into x.grad and records dgamma/dbeta.
-        sums: BN-backward reductions already made by the data-gradient convolution's epilogue."""
+    def _bn_backward(self, ctx, x, bn_name, relu, da, aff):
+        """dL/d(act(bn(x))) = da  ->  accumulates dL/dx into x.grad and records dgamma/dbeta."""
         m = self.bns[bn_name].mod
         scale, shift, mean, invstd, batch = aff
         tgt = x.accum_target()
         if batch:
             dx, dgamma, dbeta = ops.bn_bwd(da, x.data, mean, invstd, scale, shift, m.weight.detach(), relu,
-                                           accumulate_into=tgt, sums=sums)
+                                           accumulate_into=tgt)
             ctx.pgrads[m.weight] = dgamma
             ctx.pgrads[m.bias] = dbeta
         else:  # eval-mode affine: statistics are constants, so no batch-statistics terms in dx
@@ -365,19 +364,12 @@ class Engine:
                 if not need_dx:
                     return
                 # ---- data gradient w.r.t. the conv input a = act(bn(x))
-                bn_sums = None
                 if c.tc_dgrad:
                     wd_hi, wd_lo, use_h = ctx.weights.dgrad(c, dy.shape[1], dy.shape[2], f16_ok=dy_scale is not None)
                     if FUSED_DGRAD:
                         if use_h:
-                            f16_scale = dy_scale if wd_hi.dtype == torch.float16 else None
-                            if (ops.CONV_BNBWD and bn_name is not None and aff[4] and c.cin <= 128
-                                    and x.data.shape[-1] == c.cin):
-                                # the conv epilogue also reduces the two BatchNorm-backward sums over (da, x)
-                                da, bn_sums = ops.conv2d_tc_h_dgrad_bnbwd(dy, wd_hi, wd_lo, c.k, x.data, aff[2], aff[3],
-                                                                          aff[0], aff[1], relu, in_scale=f16_scale)
-                            else:
-                                da = ops.conv2d_tc_h(dy, wd_hi, wd_lo, c.k, in_scale=f16_scale)
+                            da = ops.conv2d_tc_h(dy, wd_hi, wd_lo, c.k,
+                                                 in_scale=dy_scale if wd_hi.dtype == torch.float16 else None)
                         else:
                             da = ops.conv2d_tc_fused(dy, wd_hi, wd_lo, c.k)
                     else:
@@ -385,7 +377,7 @@ class Engine:
                 else:
                     da = ops.conv2d_simt_dgrad(dy, c.weight.detach(), x.data.shape[1:3], stride=c.stride, pad=c.pad)
                 if bn_name is not None:
-                    self._bn_backward(ctx, x, bn_name, relu, da, aff, sums=bn_sums)
+                    self._bn_backward(ctx, x, bn_name, relu, da, aff)
                 else:
                     x.add_grad(da, owned=True)
             ctx.tape.append(bwd)

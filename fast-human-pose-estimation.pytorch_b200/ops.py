@@ -186,28 +186,6 @@ def weight_prep_f16(w_oihw, for_dgrad=False, split=True):
     return hi, lo
 
 
-# BN-backward sums in the data-gradient conv epilogue: correct (tests/test_ops_gpu.py) but measured SLOWER end to end
-# (37.2 vs 33.1 ms/step: the epilogue's reads of the BN input put the dgrad kernels, which sit on the backward critical
-# path, behind HBM latency), so off by default.
-CONV_BNBWD = os.environ.get("FPD_CONV_BNBWD", "0") != "0"
-
-
-def conv2d_tc_h_dgrad_bnbwd(dy, w_hi, w_lo, ksize, bn_x, mean, invstd, scale, shift, relu, in_scale=None):
-    """da = dgrad conv of dy (weights in the dgrad layout) AND the BatchNorm-backward sums of the BN whose output
-    gradient da is: returns (da, sums[2C]) with sums[:C] = sum dz, sums[C:] = sum dz * xhat (dz = da masked by ReLU)."""
-    B, H, W, Cin = dy.shape
-    Cout = w_hi.shape[1]
-    f16 = w_hi.dtype == torch.float16
-    da = torch.empty((B, H, W, Cout), dtype=torch.float32, device=dy.device)
-    sums = torch.empty(2 * Cout, dtype=torch.float32, device=dy.device)
-    ws = _ws.get(N.lib().fpd_sm_count() * 2 * Cout * 4, dy.device)
-    N.check(N.lib().fpd_conv2d_tc_h_dgrad_bnbwd(_p(dy), _p(w_hi), _p(w_lo), int(f16), _p(da), 1.0, _p(in_scale), _p(bn_x),
-                                                _p(mean), _p(invstd), _p(scale), _p(shift), int(relu), _p(sums), _p(ws),
-                                                ws.numel(), B, H, W, Cin, Cout, ksize, _stream()),
-            "conv2d_tc_h_dgrad_bnbwd")
-    return da, sums
-
-
 def weight_prep_f16_both(w_oihw):
     """-> ((fwd_hi, fwd_lo), (dgrad_hi, dgrad_lo)) in one launch."""
     _chk(w_oihw, "w")
@@ -364,13 +342,11 @@ def bn_bwd_reduce(da, x, mean, invstd, scale, shift, relu):
     return sums
 
 
-def bn_bwd(da, x, mean, invstd, scale, shift, gamma, relu, accumulate_into=None, sums=None):
-    """Returns (dx, dgamma, dbeta) for y = relu?(bn(x)) given da = dL/dy (train-mode batch statistics).
-    sums: the two per-channel reductions if the producer of da already made them (conv2d_tc_h_dgrad_bnbwd)."""
+def bn_bwd(da, x, mean, invstd, scale, shift, gamma, relu, accumulate_into=None):
+    """Returns (dx, dgamma, dbeta) for y = relu?(bn(x)) given da = dL/dy (train-mode batch statistics)."""
     C = x.shape[-1]
     P = x.numel() // C
-    if sums is None:
-        sums = bn_bwd_reduce(da, x, mean, invstd, scale, shift, relu)
+    sums = bn_bwd_reduce(da, x, mean, invstd, scale, shift, relu)
     dx = accumulate_into if accumulate_into is not None else torch.empty_like(x)
     N.check(N.lib().fpd_bn_bwd_apply(_p(da), _p(x), _p(mean), _p(invstd), _p(scale), _p(shift), _p(gamma), int(relu),
                                      _p(sums), int(accumulate_into is not None), _p(dx), P, C, _stream()),

@@ -98,17 +98,6 @@ int fpd_conv2d_tc_h(const float* x, const float* pre_mean, const float* pre_scal
                     int pre_relu, const void* w_hi, const void* w_lo, int f16, const float* bias,
                     const float* residual, const float* relu_mask, float* y, float out_scale, const float* in_scale,
                     int B, int H, int W, int Cin, int Cout, int ksize, fpd_stream_t stream);
-/* Data-gradient convolution (fpd_conv2d_tc_h on dY with the flipped weights, no pre-op) that ALSO reduces, in its
- * epilogue, the two per-channel sums BatchNorm backward needs for the BN whose output gradient it produces:
- *   sums[0:C] = sum dz, sums[C:2C] = sum dz * (bn_x - mean) * invstd,  dz = da masked by the ReLU of the BN output
- * (C = Cout <= 128; bn_x is the BN input, same shape as da). Replaces the separate pass of fpd_bn_bwd_reduce over
- * (da, bn_x): BatchNorm2d + ReLU backward of lib/models/hourglass.py:34-44 under loss.backward().
- * workspace: fpd_sm_count() * 2 * Cout floats. Deterministic (fixed summation order). */
-int fpd_conv2d_tc_h_dgrad_bnbwd(const float* dy, const void* w_hi, const void* w_lo, int f16, float* da, float out_scale,
-                                const float* in_scale, const float* bn_x, const float* bn_mean, const float* bn_invstd,
-                                const float* bn_scale, const float* bn_shift, int bn_relu, float* sums, void* workspace,
-                                size_t workspace_bytes, int B, int H, int W, int Cin, int Cout, int ksize,
-                                fpd_stream_t stream);
 /* Forward ([tap][O][I]) and data-gradient ([taps-1-tap][I][O]) __half hi/lo forms of w * 2^8 from one read of the
  * weights: one launch per convolution and training step instead of two. */
 int fpd_weight_prep_f16_both(const float* w_oihw, void* f_hi, void* f_lo, void* d_hi, void* d_lo, int O, int I, int k,

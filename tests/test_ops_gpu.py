@@ -190,37 +190,6 @@ def test_conv2d_tc_h_f16_dgrad_with_amax_scale(mag):
     assert relerr(bias_grad, nchw(dy).sum(dim=(0, 2, 3))) < 1e-5
 
 
-@pytest.mark.parametrize("shape", [(2, 64, 64, 64, 64, 3), (2, 32, 32, 128, 64, 1), (3, 8, 8, 64, 128, 1), (8, 4, 4, 64, 64, 3),
-                                   (2, 64, 48, 32, 32, 3), (2, 16, 16, 128, 16, 1)])
-@pytest.mark.parametrize("f16", [False, True])
-def test_conv2d_tc_h_dgrad_with_fused_bn_backward_sums(shape, f16):
-    """Data-gradient conv whose epilogue also reduces the BatchNorm-backward sums (sum dz, sum dz*xhat) over (da, x):
-    da must equal the plain launch bit for bit, the sums must match the separate two-stage reduction."""
-    B, H, W, Cdy, Cx, k = shape          # dY has Cdy channels, the conv input / BN tensor x has Cx
-    o = ops()
-    if not o.N.lib().fpd_conv2d_tc_h_supported(Cdy, Cx, k, H, W, int(f16)):
-        pytest.skip("shape not taken by conv_tc_h")
-    g = torch.Generator(device="cuda").manual_seed(21)
-    dy = torch.randn(B, H, W, Cdy, device="cuda", generator=g) * 1e-3
-    x = torch.randn(B, H, W, Cx, device="cuda", generator=g) * 2 + 0.5
-    w = torch.randn(Cdy, Cx, k, k, device="cuda", generator=g) * (1.0 / (Cx * k * k) ** 0.5)   # forward conv Cx -> Cdy
-    mean = x.reshape(-1, Cx).mean(0)
-    invstd = 1.0 / torch.sqrt(x.reshape(-1, Cx).var(0, unbiased=False) + 1e-5)
-    gamma = torch.rand(Cx, device="cuda", generator=g) + 0.5
-    scale, shift = gamma * invstd, torch.randn(Cx, device="cuda", generator=g) * 0.3
-    prep = o.weight_prep_f16 if f16 else o.weight_prep
-    w_hi, w_lo = prep(w, for_dgrad=True)
-    in_scale = o.channel_sum(dy, want_amax=True)[1] if f16 else None
-    da_ref = o.conv2d_tc_h(dy, w_hi, w_lo, k, in_scale=in_scale)
-    for relu in (True, False):
-        da, sums = o.conv2d_tc_h_dgrad_bnbwd(dy, w_hi, w_lo, k, x, mean, invstd, scale, shift, relu, in_scale=in_scale)
-        sums_ref = o.bn_bwd_reduce(da_ref, x, mean, invstd, scale, shift, relu)
-        torch.cuda.synchronize()
-        assert torch.equal(da, da_ref)
-        err = ((sums - sums_ref).abs().max() / sums_ref.abs().max()).item()
-        assert err < 2e-5, "fused BN-backward sums %s f16=%s relu=%s: %.3e" % (shape, f16, relu, err)
-
-
 @pytest.mark.parametrize("shape", [(2, 64, 64, 64, 64, 3), (2, 32, 32, 128, 64, 1), (4, 8, 8, 64, 128, 1)])
 def test_conv2d_tc_dgrad_with_relu_mask(shape):
     B, H, W, Cin, Cout, k = shape
