@@ -192,7 +192,7 @@ struct BnFinalize {
 // Second stage of the BN statistics + the BatchNorm finalize of one consuming module in ONE kernel (was two): per
 // channel, mean = sum_b n_b mean_b / P, then M2 = sum_b M2_b + n_b (mean_b - mean)^2 over the block partials of
 // bn_stats_partial_kernel, in fp64 and a fixed order (deterministic; no division inside the loops, unlike the sequential
-// Chan merge of bn_stats_final_kernel whose fp64 divide chain cost ~7 us per launch). One warp per 4 channels.
+// Chan merge of bn_stats_final_kernel whose fp64 divide chain cost ~7 us per launch). One 256-thread block per 4 channels.
 // Reference semantics: nn.BatchNorm2d in train mode incl. the running-statistics update (lib/models/hourglass.py:18-26).
 __global__ void __launch_bounds__(256)
 bn_stats_final_finalize_kernel(const double* __restrict__ part, int nblocks, int64_t rows_per_block, int64_t P, int C,

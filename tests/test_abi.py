@@ -49,5 +49,38 @@ def test_every_host_module_imports_on_cpu():
     import ast
     for script in ("bench.py", "__graft_entry__.py", "tools/profile_step.py", "tools/profile_kernel.py",
                    "tools/profile_convs.py", "tools/bench_conv_variants.py", "tools/diag_net.py", "tools/diag_grad.py",
-                   "tools/summarize_profiles.py"):
+                   "tools/summarize_profiles.py", "tools/diag_conv_h.py", "tools/diag_wgrad.py", "tools/diag_wgrad3.py",
+                   "tools/diag_wgrad_shift.py"):
         ast.parse(open(os.path.join(ROOT, script)).read(), script)
+
+
+def test_kernel_shape_planners_on_cpu():
+    """The support predicates of the generation-5 conv kernel and the halo weight-gradient kernel are pure host code
+    (shared-memory / TMEM plans): every shape of the BASELINE configs must be taken, the documented exceptions not."""
+    import fpd_b200  # noqa: F401
+    from fpd_b200 import _native as N
+    lib = N.lib()
+    # hourglass student (64/128 ch) and teacher (128/256 ch) convolutions at every level, both operand encodings
+    for hw in (64, 32, 16, 8, 4):
+        for (cin, cout, k) in ((64, 64, 3), (128, 128, 3), (128, 64, 1), (64, 128, 1), (256, 128, 1), (128, 256, 1),
+                               (256, 256, 1), (256, 16, 1), (16, 256, 1), (128, 16, 1), (16, 128, 1)):
+            for f16 in (0, 1):
+                assert lib.fpd_conv2d_tc_h_supported(cin, cout, k, hw, hw, f16) == 1, (cin, cout, k, hw, f16)
+    assert lib.fpd_conv2d_tc_h_supported(32, 32, 3, 128, 128, 1) == 1          # stem bottleneck at 128x128
+    assert lib.fpd_conv2d_tc_h_supported(160, 32, 1, 128, 128, 1) == 1         # 7x7 stem as im2col (K padded to 160)
+    assert lib.fpd_conv2d_tc_h_supported(64, 64, 3, 64, 48, 1) == 1            # HRNet resolution
+    assert lib.fpd_conv2d_tc_h_supported(3, 32, 7, 256, 256, 0) == 0           # raw 7x7 stem: not a tensor-core shape
+    assert lib.fpd_conv2d_tc_h_supported(64, 64, 5, 64, 64, 0) == 0
+    assert lib.fpd_conv2d_tc_h_supported(6, 64, 1, 64, 64, 1) == 0             # fp16 rows need Cin % 8 == 0 ...
+    assert lib.fpd_conv2d_tc_h_supported(12, 64, 1, 64, 64, 0) == 1            # ... tf32 rows Cin % 4 == 0
+    assert lib.fpd_conv2d_tc_h_supported(64, 24, 1, 64, 64, 0) == 0            # Cout % 16
+    # halo weight-gradient kernel: 3x3, Cin in {64, 128}, W % 8 == 0, at least two pipeline stages must fit
+    for hw in (64, 32, 16, 8):
+        assert lib.fpd_conv2d_wgrad_tc3_supported(hw, hw, 64, 64, 3) == 1
+    assert lib.fpd_conv2d_wgrad_tc3_supported(64, 48, 64, 32, 3) == 1
+    assert lib.fpd_conv2d_wgrad_tc3_supported(4, 4, 64, 64, 3) == 0            # a K step must be 8 pixels along w
+    assert lib.fpd_conv2d_wgrad_tc3_supported(64, 64, 32, 32, 3) == 0          # M = Cin must be 64 or 128
+    assert lib.fpd_conv2d_wgrad_tc3_supported(64, 64, 64, 64, 1) == 0          # 1x1: wgrad_tc2
+    assert lib.fpd_conv2d_wgrad_tc3_supported(32, 32, 128, 128, 3) == 0        # one stage only: wgrad_tc2
+    # workspace of the dispatching entry point covers whichever kernel runs
+    assert lib.fpd_conv2d_wgrad_tc_workspace_bytes(32, 64, 64, 64, 64, 3) >= 9 * 64 * 64 * 4
