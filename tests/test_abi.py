@@ -84,3 +84,26 @@ def test_kernel_shape_planners_on_cpu():
     assert lib.fpd_conv2d_wgrad_tc3_supported(32, 32, 128, 128, 3) == 0        # one stage only: wgrad_tc2
     # workspace of the dispatching entry point covers whichever kernel runs
     assert lib.fpd_conv2d_wgrad_tc_workspace_bytes(32, 64, 64, 64, 64, 3) >= 9 * 64 * 64 * 4
+
+
+def test_bench_reference_arm_contract_on_cpu(capsys):
+    """`bench.py --impl reference` (the oracle port of the FPD step on the host cores) prints one JSON line with the
+    contract's keys; runs here without a GPU (one short timed step)."""
+    import json
+    import sys
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+    os.environ["FPD_CPU_THREADS"] = str(min(8, len(os.sched_getaffinity(0))))
+    try:
+        bench.run_reference(types.SimpleNamespace(steps=1, warmup=0, gpus=1), rank=0)
+    finally:
+        os.environ.pop("FPD_CPU_THREADS", None)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "images/sec" and line["unit"] == "images/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["n_gpus"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    # other ranks of a torchrun launch stay silent
+    bench.run_reference(types.SimpleNamespace(steps=1, warmup=0, gpus=2), rank=1)
+    assert capsys.readouterr().out == ""
