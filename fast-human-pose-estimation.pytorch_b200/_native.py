@@ -83,6 +83,10 @@ _SIGNATURES = {
     "fpd_nms_workspace_bytes": (c_size_t, [c_int]),
     "fpd_nms_device": (c_int, [P, c_int, c_int, c_float, P, P, P, c_size_t, P]),
     "fpd_nms_host": (c_int, [P, P, P, c_int, c_int, c_float, c_int]),
+    "fpd_oks_nms_device": (c_int, [P, c_int, P, P, c_int, c_int, ctypes.c_double, c_int, ctypes.c_double, P, P, P, c_size_t,
+                                   P]),
+    "fpd_oks_rescore": (c_int, [P, c_int, P, c_int, c_int, ctypes.c_double, P, P]),
+    "fpd_gaussian_targets": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "fpd_adam_flat": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P]),
 }
 

@@ -374,6 +374,23 @@ int fpd_nms_host(int* keep_out, int* num_out, const float* boxes_host, int boxes
   return rc;
 }
 
+int fpd_oks_nms_device(const void* kpts_sorted, int kpt_f64, const double* areas_sorted, const double* vars_, int n, int J,
+                       double thresh, int use_vis, double in_vis_thre, int* keep, int* num_keep, void* ws, size_t wsb,
+                       fpd_stream_t stream) {
+  return oks_nms_device(kpts_sorted, kpt_f64, areas_sorted, vars_, n, J, thresh, use_vis, in_vis_thre, keep, num_keep, ws,
+                        wsb, S(stream));
+}
+int fpd_oks_rescore(const void* kpts, int kpt_f64, const double* box_score, int n, int J, double in_vis_thre, double* out,
+                    fpd_stream_t stream) {
+  return oks_rescore(kpts, kpt_f64, box_score, n, J, in_vis_thre, out, S(stream));
+}
+int fpd_gaussian_targets(const float* joints, const float* joints_vis, const float* joints_weight, const float* gauss_table,
+                         float* target, float* target_weight, int N, int J, int H, int W, int image_w, int image_h,
+                         int sigma, fpd_stream_t stream) {
+  return gaussian_targets(joints, joints_vis, joints_weight, gauss_table, target, target_weight, N, J, H, W, image_w,
+                          image_h, sigma, S(stream));
+}
+
 int fpd_adam_flat(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float b1, float b2,
                   float eps, float wd, int step, float grad_scale, fpd_stream_t stream) {
   return adam_flat(param, grad, m, v, n, lr, b1, b2, eps, wd, step, grad_scale, S(stream));

@@ -171,6 +171,20 @@ size_t nms_workspace_bytes(int n);
 int nms_device(const float* boxes_sorted_dev, int n, int box_dim, float thresh, int* keep_dev, int* num_keep_dev,
                void* workspace, size_t ws_bytes, cudaStream_t stream);
 
+// OKS-NMS (lib/nms/nms.py:75-124): kpts [n,J,3] (x,y,score; float or double) sorted by person score descending,
+// areas [n], vars_[J] = (2 sigma_j)^2 as float64; keep/num_keep as nms_device. use_vis: mask joints by the candidate's
+// score > in_vis_thre.
+int oks_nms_device(const void* kpts_sorted, int kpt_f64, const double* areas_sorted, const double* vars_, int n, int J,
+                   double thresh, int use_vis, double in_vis_thre, int* keep_dev, int* num_keep_dev, void* workspace,
+                   size_t ws_bytes, cudaStream_t stream);
+// person rescoring (lib/dataset/coco.py:346-357): out[i] = box_score[i] * mean(score_j | score_j > in_vis_thre)
+int oks_rescore(const void* kpts, int kpt_f64, const double* box_score, int n, int J, double in_vis_thre, double* out,
+                cudaStream_t stream);
+// Gaussian heat-map targets (lib/dataset/JointsDataset.py:233-289) for N samples
+int gaussian_targets(const float* joints, const float* joints_vis, const float* joints_weight, const float* gauss_table,
+                     float* target, float* target_weight, int N, int J, int H, int W, int image_w, int image_h, int sigma,
+                     cudaStream_t stream);
+
 // ---- adam.cu ----
 int adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
               float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream);

@@ -480,3 +480,65 @@ def adam_flat(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_de
     N.check(N.lib().fpd_adam_flat(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr),
                                   float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
                                   float(grad_scale), _stream()), "adam_flat")
+
+
+def oks_nms_device(kpts_sorted, areas_sorted, thresh, sigmas=None, in_vis_thre=None):
+    """OKS-NMS on the device (csrc/nms.cu; reference lib/nms/nms.py:75-124). kpts_sorted: CUDA [n,J,3] float32 or float64
+    (x, y, score), persons sorted by score descending; areas_sorted: CUDA float64 [n]. Returns (keep int32[n], num int32[1])
+    device tensors -- indices into the sorted list, best first."""
+    n, J = kpts_sorted.shape[0], kpts_sorted.shape[1]
+    dev = kpts_sorted.device
+    assert kpts_sorted.dtype in (torch.float32, torch.float64) and kpts_sorted.is_contiguous()
+    areas = areas_sorted.to(torch.float64).contiguous()
+    if sigmas is None:
+        sigmas = COCO_SIGMAS
+    vars_ = (torch.as_tensor(sigmas, dtype=torch.float64) * 2) ** 2
+    vars_ = vars_.to(dev)
+    keep = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    num = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _ws.get(N.lib().fpd_nms_workspace_bytes(n), dev)
+    N.check(N.lib().fpd_oks_nms_device(_p(kpts_sorted), int(kpts_sorted.dtype == torch.float64), _p(areas), _p(vars_), n, J,
+                                       float(thresh), int(in_vis_thre is not None),
+                                       float(in_vis_thre if in_vis_thre is not None else 0.0), _p(keep), _p(num), _p(ws),
+                                       ws.numel(), _stream()), "oks_nms_device")
+    return keep, num
+
+
+# lib/nms/nms.py:77: per-joint falloff constants of the COCO key-point metric
+COCO_SIGMAS = [x / 10.0 for x in (.26, .25, .25, .35, .35, .79, .79, .72, .72, .62, .62, 1.07, 1.07, .87, .87, .89, .89)]
+
+
+def oks_rescore(kpts, box_score, in_vis_thre):
+    """out[i] = box_score[i] * mean(joint scores above in_vis_thre) (lib/dataset/coco.py:346-357); float64 CUDA tensor."""
+    n, J = kpts.shape[0], kpts.shape[1]
+    assert kpts.dtype in (torch.float32, torch.float64) and kpts.is_contiguous()
+    bs = box_score.to(torch.float64).contiguous()
+    out = torch.empty(n, dtype=torch.float64, device=kpts.device)
+    N.check(N.lib().fpd_oks_rescore(_p(kpts), int(kpts.dtype == torch.float64), _p(bs), n, J, float(in_vis_thre), _p(out),
+                                    _stream()), "oks_rescore")
+    return out
+
+
+def gaussian_targets(joints, joints_vis, heatmap_size, image_size, sigma=2, joints_weight=None, gauss_table=None):
+    """Batch form of JointsDataset.generate_target (lib/dataset/JointsDataset.py:233-289). joints / joints_vis: CUDA float32
+    [N,J,3]; heatmap_size / image_size: (w, h). Returns (target [N,J,h,w], target_weight [N,J,1])."""
+    import numpy as np
+    _chk(joints, "joints")
+    _chk(joints_vis, "joints_vis")
+    n, J = joints.shape[0], joints.shape[1]
+    W, H = int(heatmap_size[0]), int(heatmap_size[1])
+    dev = joints.device
+    if gauss_table is None:
+        # the reference's own expression (float32 numpy), so the stamped patch is bit-identical: JointsDataset.py:266-272
+        size = 2 * (sigma * 3) + 1
+        xs = np.arange(0, size, 1, np.float32)
+        ys = xs[:, np.newaxis]
+        x0 = y0 = size // 2
+        g = np.exp(- ((xs - x0) ** 2 + (ys - y0) ** 2) / (2 * sigma ** 2))
+        gauss_table = torch.from_numpy(np.ascontiguousarray(g, dtype=np.float32)).to(dev)
+    target = torch.empty((n, J, H, W), dtype=torch.float32, device=dev)
+    tw = torch.empty((n, J, 1), dtype=torch.float32, device=dev)
+    jw = None if joints_weight is None else joints_weight.to(dev).float().contiguous().reshape(-1)
+    N.check(N.lib().fpd_gaussian_targets(_p(joints), _p(joints_vis), _p(jw), _p(gauss_table), _p(target), _p(tw), n, J, H, W,
+                                         int(image_size[0]), int(image_size[1]), int(sigma), _stream()), "gaussian_targets")
+    return target, tw

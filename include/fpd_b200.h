@@ -264,6 +264,29 @@ int fpd_nms_device(const float* boxes_sorted, int n, int box_dim, float thresh, 
 int fpd_nms_host(int* keep_out_host, int* num_out_host, const float* boxes_host, int boxes_num, int boxes_dim,
                  float nms_overlap_thresh, int device_id);
 
+/* OKS-NMS. Replaces the host numpy loops of lib/nms/nms.py:75-96 (oks_iou) and :99-124 (oks_nms), called from
+ * lib/dataset/coco.py:359-369. kpts_sorted: device [n,J,3] (x, y, score), float32 (kpt_f64 = 0, what coco.py:283 holds)
+ * or float64, persons sorted by score descending; areas_sorted: device double[n]; vars: device double[J] = (2 sigma_j)^2;
+ * a person j is suppressed when oks(kept i, j) > thresh; use_vis != 0 masks joints by the candidate's score >
+ * in_vis_thre (nms.py:90-92). keep / num_keep / workspace as fpd_nms_device (fpd_nms_workspace_bytes(n)). */
+int fpd_oks_nms_device(const void* kpts_sorted, int kpt_f64, const double* areas_sorted, const double* vars, int n, int J,
+                       double thresh, int use_vis, double in_vis_thre, int* keep, int* num_keep, void* workspace,
+                       size_t workspace_bytes, fpd_stream_t stream);
+/* Person rescoring before OKS-NMS, lib/dataset/coco.py:346-357: out[i] = box_score[i] * mean of the joint scores above
+ * in_vis_thre (0 if none). kpts: device [n,J,3]; box_score, out: device double[n]. */
+int fpd_oks_rescore(const void* kpts, int kpt_f64, const double* box_score, int n, int J, double in_vis_thre, double* out,
+                    fpd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Target generation. Replaces JointsDataset.generate_target, lib/dataset/JointsDataset.py:233-289, for a whole batch:
+ * joints, joints_vis: device float[N,J,3]; joints_weight: device float[J] or NULL (USE_DIFFERENT_JOINTS_WEIGHT);
+ * gauss_table: device float[(6 sigma + 1)^2], the reference's un-normalised Gaussian patch; outputs target
+ * float[N,J,H,W] (fully written) and target_weight float[N,J]. image_w/h and W/H give feat_stride.
+ * ------------------------------------------------------------------------------------------------- */
+int fpd_gaussian_targets(const float* joints, const float* joints_vis, const float* joints_weight, const float* gauss_table,
+                         float* target, float* target_weight, int N, int J, int H, int W, int image_w, int image_h,
+                         int sigma, fpd_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Optimizer. Replaces torch.optim.Adam as configured by lib/utils/utils.py:69-73, stepped at
  * lib/core/function.py:147, over one flat parameter buffer.

@@ -49,7 +49,118 @@ def gaussian_targets(rng, B, J, h, w):
     return t
 
 
+def main_decode2():
+    """Section 6: the host-side decode tail the drop-in replaces -- get_final_preds (inference.py:49-79, POST_PROCESS on
+    and off, non-trivial centre / scale, via the reference's cv2 affine), accuracy (evaluate.py:41-71), and OKS-NMS with
+    the rescoring loop of lib/dataset/coco.py:334-369 (nms.py:75-124). Own RNG: does not disturb the other vectors."""
+    sys.path.insert(0, os.path.join(REF, "lib"))
+    from core.inference import get_final_preds, get_max_preds   # noqa: E402
+    from core.evaluate import accuracy                           # noqa: E402
+    src = open(os.path.join(REF, "lib/nms/nms.py")).read().replace("from .cpu_nms import cpu_nms", "").replace(
+        "from .gpu_nms import gpu_nms", "")
+    nms_ns = {}
+    exec(compile(src, "ref_nms.py", "exec"), nms_ns)
+    rng = np.random.RandomState(7)
+    save = {}
+    for tag, (B, J, h, w) in (("sq", (3, 16, 64, 64)), ("rect", (3, 17, 64, 48))):
+        # peaky maps: low noise + a Gaussian bump per joint (some at the border, one all-negative, one flat)
+        hm = (rng.randn(B, J, h, w) * 0.05).astype(np.float32)
+        hm += gaussian_targets(rng, B, J, h, w) * rng.uniform(0.3, 1.0, (B, J, 1, 1)).astype(np.float32)
+        hm[0, 0] = -0.5
+        hm[0, 1] = 0.25
+        hm[1, 2, 0, 0] = 3.0          # arg-max in the corner: no quarter-pixel nudge
+        hm[1, 3, h - 1, w - 1] = 3.0
+        hm[2, 4, 1, 1] = 3.0          # px == 1: excluded by the strict 1 < px test
+        hm[2, 5, 2, 2] = 3.0          # first position that is nudged
+        center = np.stack([rng.uniform(100, 900, B), rng.uniform(100, 700, B)], 1).astype(np.float32)
+        sc = rng.uniform(0.6, 3.2, B).astype(np.float32)
+        scale = np.stack([sc, sc * (1.0 if tag == "sq" else 1.25)], 1).astype(np.float32)
+        save[tag + "/hm"] = hm
+        save[tag + "/center"] = center
+        save[tag + "/scale"] = scale
+        for pp in (True, False):
+            cfgt = NS(TEST=NS(POST_PROCESS=pp))
+            preds, maxvals = get_final_preds(cfgt, hm.copy(), center, scale)
+            save["%s/preds_pp%d" % (tag, int(pp))] = preds
+            save["%s/maxvals_pp%d" % (tag, int(pp))] = maxvals
+        # accuracy(): output = hm, target = clean Gaussians (some joints with target arg-max <= 1 -> ignored)
+        tgt = gaussian_targets(rng, B, J, h, w)
+        tgt[0, 2] = 0.0
+        tgt[1, 3] = 0.0
+        tgt[1, 3, 0, 5] = 1.0
+        tgt[:, 6] = 0.0               # a joint ignored in every sample: acc = -1, not counted
+        sig = rng.choice([0.1, 0.3, 0.45], size=(B, J, 1, 1)).astype(np.float32)
+        out = tgt + (rng.randn(B, J, h, w).astype(np.float32) * sig)
+        acc, avg, cnt, pred = accuracy(out, tgt)
+        save[tag + "/acc_out"] = out
+        save[tag + "/acc_target"] = tgt
+        save[tag + "/acc"] = acc
+        save[tag + "/avg_acc"] = np.float64(avg)
+        save[tag + "/cnt"] = np.int64(cnt)
+        save[tag + "/acc_pred"] = pred
+    # OKS-NMS + rescoring (coco.py:343-369): persons of one image
+    for tag, n in (("oks_a", 40), ("oks_b", 7), ("oks_c", 1)):
+        base = rng.uniform(50, 400, (max(n // 4, 1), 17, 2))
+        kp = np.zeros((n, 17, 3), np.float64)
+        for i in range(n):
+            kp[i, :, :2] = base[i % base.shape[0]] + rng.randn(17, 2) * rng.choice([1.0, 6.0, 40.0])
+            kp[i, :, 2] = rng.uniform(0.0, 1.0, 17)
+        area = rng.uniform(2000, 40000, n)
+        box_score = rng.uniform(0.1, 1.0, n)
+        in_vis_thre, oks_thre = 0.2, 0.9
+        db = []
+        for i in range(n):
+            ks, vn = 0.0, 0
+            for j in range(17):
+                if kp[i, j, 2] > in_vis_thre:
+                    ks += kp[i, j, 2]
+                    vn += 1
+            if vn:
+                ks /= vn
+            db.append({"keypoints": kp[i], "area": area[i], "score": ks * box_score[i]})
+        keep = nms_ns["oks_nms"](db, oks_thre)
+        save[tag + "/kpts"] = kp
+        save[tag + "/area"] = area
+        save[tag + "/box_score"] = box_score
+        save[tag + "/rescored"] = np.array([d["score"] for d in db])
+        save[tag + "/keep"] = np.array(keep, np.int64)
+        save[tag + "/keep_vis"] = np.array(nms_ns["oks_nms"](db, 0.5, None, 0.3), np.int64)
+    # Gaussian target generation (lib/dataset/JointsDataset.py:233-289), called unbound on a stub `self`
+    JointsDataset = load("ref_joints_dataset", "lib/dataset/JointsDataset.py").JointsDataset   # dataset/__init__ needs json_tricks
+    for tag, (J, img, hms, diffw) in (("tgt_sq", (16, (256, 256), (64, 64), False)),
+                                      ("tgt_rect", (17, (192, 256), (48, 64), True))):
+        stub = NS(num_joints=J, target_type="gaussian", heatmap_size=np.array(hms), image_size=np.array(img), sigma=2,
+                  use_different_joints_weight=diffw,
+                  joints_weight=np.array([1., 1., 1., 1., 1., 1., 1., 1.2, 1.2, 1.5, 1.5, 1., 1., 1.2, 1.2, 1.5, 1.5],
+                                         np.float32).reshape(17, 1)[:J])
+        n = 12
+        joints = np.zeros((n, J, 3), np.float32)
+        joints[:, :, 0] = rng.uniform(-20, img[0] + 20, (n, J))     # some centres off the image
+        joints[:, :, 1] = rng.uniform(-20, img[1] + 20, (n, J))
+        joints[0, 0, :2] = (-40.0, 10.0)                            # Gaussian entirely out of bounds -> weight 0
+        joints[0, 1, :2] = (img[0] + 39.9, 30.0)
+        joints[0, 2, :2] = (1.9, 2.1)                               # rounding of mu = int(x / stride + 0.5)
+        joints[0, 3, :2] = (img[0] - 0.1, img[1] - 0.1)
+        vis = np.zeros((n, J, 3), np.float32)
+        vis[:, :, 0] = vis[:, :, 1] = (rng.rand(n, J) > 0.25).astype(np.float32)
+        tg, tw = [], []
+        for i in range(n):
+            t_, w_ = JointsDataset.generate_target(stub, joints[i], vis[i])
+            tg.append(t_)
+            tw.append(w_)
+        save[tag + "/joints"] = joints
+        save[tag + "/joints_vis"] = vis
+        save[tag + "/target"] = np.stack(tg)
+        save[tag + "/target_weight"] = np.stack(tw)
+    save["oks/in_vis_thre"] = np.float64(0.2)
+    save["oks/oks_thre"] = np.float64(0.9)
+    np.savez_compressed(os.path.join(OUT, "decode2.npz"), **save)
+    print("decode2.npz", os.path.getsize(os.path.join(OUT, "decode2.npz")))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "decode2":
+        return main_decode2()
     torch.set_num_threads(4)
     hg = load("ref_hourglass", "lib/models/hourglass.py")
     loss_mod = load("ref_loss", "lib/core/loss.py")
@@ -215,6 +326,7 @@ def main():
         save["out_eval"] = hnet(hx).numpy()
     np.savez_compressed(os.path.join(OUT, "hrnet_small.npz"), **save)
 
+    main_decode2()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))
