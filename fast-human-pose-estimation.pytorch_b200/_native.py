@@ -72,6 +72,7 @@ _SIGNATURES = {
     "fpd_upsample2x_add": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     "fpd_upsample2x_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "fpd_nchw_to_nhwc": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "fpd_nchw_to_nhwc_flipw": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "fpd_nhwc_to_nchw": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "fpd_add": (c_int, [P, P, P, c_int64, P]),
     "fpd_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

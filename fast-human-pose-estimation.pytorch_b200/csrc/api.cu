@@ -285,6 +285,9 @@ int fpd_upsample2x_bwd(const float* dout, float* dlow, int B, int H, int W, int 
 int fpd_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, fpd_stream_t stream) {
   return nchw_to_nhwc(x, y, B, C, H, W, S(stream));
 }
+int fpd_nchw_to_nhwc_flipw(const float* x, float* y, int B, int C, int H, int W, fpd_stream_t stream) {
+  return nchw_to_nhwc_flipw(x, y, B, C, H, W, S(stream));
+}
 int fpd_nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, fpd_stream_t stream) {
   return nhwc_to_nchw(x, y, B, C, H, W, S(stream));
 }

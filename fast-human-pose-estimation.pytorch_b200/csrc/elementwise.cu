@@ -632,8 +632,9 @@ __global__ void upsample2x_bwd_kernel(const float4* __restrict__ dout, float4* _
 }
 
 // NCHW <-> NHWC through a 32x33 shared-memory transpose tile (coalesced on both sides)
-__global__ void transpose_cs_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
-  // in: [batch][rows][cols] -> out: [batch][cols][rows]
+__global__ void transpose_cs_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols, int flip_w) {
+  // in: [batch][rows][cols] -> out: [batch][cols][rows]; flip_w > 0 (NCHW -> NHWC only): cols = H * flip_w pixels and the
+  // output pixel of input pixel (h, w) is (h, flip_w - 1 - w) -- the W-mirrored image of the flip test (function.py:220)
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const float* src = in + (size_t)b * rows * cols;
@@ -646,7 +647,10 @@ __global__ void transpose_cs_kernel(const float* __restrict__ in, float* __restr
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int c = c0 + j, r = r0 + threadIdx.x;
-    if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][j];
+    if (r < rows && c < cols) {
+      const int co = flip_w > 0 ? (c / flip_w) * flip_w + (flip_w - 1 - c % flip_w) : c;
+      dst[(size_t)co * rows + r] = tile[threadIdx.x][j];
+    }
   }
 }
 
@@ -922,14 +926,21 @@ int upsample2x_bwd(const float* dout, float* dlow, int B, int H, int W, int C, c
 int nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream) {
   // per image: [C][HW] -> [HW][C]
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  transpose_cs_kernel<<<grid, block, 0, stream>>>(x, y, C, H * W);
+  transpose_cs_kernel<<<grid, block, 0, stream>>>(x, y, C, H * W, 0);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int nchw_to_nhwc_flipw(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream) {
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  transpose_cs_kernel<<<grid, block, 0, stream>>>(x, y, C, H * W, W);
   FPD_LAUNCH_CHECK();
   return FPD_OK;
 }
 
 int nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream) {
   dim3 grid((C + 31) / 32, (H * W + 31) / 32, B), block(32, 8);
-  transpose_cs_kernel<<<grid, block, 0, stream>>>(x, y, H * W, C);
+  transpose_cs_kernel<<<grid, block, 0, stream>>>(x, y, H * W, C, 0);
   FPD_LAUNCH_CHECK();
   return FPD_OK;
 }

@@ -109,6 +109,7 @@ int upsample2x_add(const float* up1, const float* low, float* out, int B, int H,
                    cudaStream_t stream);  // H,W = output size
 int upsample2x_bwd(const float* dout, float* dlow, int B, int H, int W, int C, cudaStream_t stream);
 int nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream);
+int nchw_to_nhwc_flipw(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream);   // + W mirror
 int nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream);
 int add_tensors(const float* a, const float* b, float* out, int64_t n, cudaStream_t stream);  // out = a + b
 size_t channel_reduce_workspace_bytes(int64_t P, int C);

@@ -180,16 +180,32 @@ class Engine:
                 self.bns[name] = BNRef(name, m)
         self._eval_cache = None
         self._eval_cache_key = None
+        self._generation = 0       # bumped by everything that writes parameters / buffers behind torch's back
         self._branch_streams = {}
+        # load_state_dict() copies in place (bumps ._version, caught by _param_version) -- but a CUDA graph that baked the
+        # pointers of the cached prepared weights would not notice, so owners of such graphs watch `generation`
+        net.register_load_state_dict_post_hook(lambda module, incompatible: self.invalidate_eval_cache())
 
     # ------------------------------------------------------------------ parameter preparation
+    @property
+    def generation(self):
+        return self._generation
+
+    def invalidate_eval_cache(self):
+        """The native kernels write parameters (fused Adam) and BatchNorm running statistics (bn_stats_fused) through raw
+        pointers, which does not bump tensor._version; a replayed CUDA graph does not even run the Python that would. Every
+        such writer calls this, so the next eval-mode forward re-derives the prepared weights and the BN affine."""
+        self._generation += 1
+        self._eval_cache = None
+        self._eval_cache_key = None
+
     def _param_version(self):
         v = 0
         for p in self.net.parameters():
             v += p._version
         for b in self.net.buffers():
             v += b._version
-        return (v, next(self.net.parameters()).device, precision_passes())
+        return (v, self._generation, next(self.net.parameters()).device, precision_passes())
 
     def _eval_prepared(self):
         key = self._param_version()
@@ -517,6 +533,7 @@ class Engine:
         if training:
             ctx.weights = PreparedWeights(ctx.passes)
             ctx.affine = None
+            self.invalidate_eval_cache()      # this forward rewrites the running statistics on the device
         else:
             w, affine = self._eval_prepared()
             if record_tape:

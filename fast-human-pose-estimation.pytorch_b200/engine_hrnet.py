@@ -125,7 +125,10 @@ class HRNetEngine(Engine):
     # ------------------------------------------------------------------ network
     def run_network(self, ctx, img_nchw):
         net = self.net
-        x = Var(ops.nchw_to_nhwc(img_nchw))
+        if ctx.shared_stem is not None and ctx.shared_stem.get("img") is img_nchw:
+            x = Var(ctx.shared_stem["nhwc"])      # layout conversion done by the caller (shared / W-mirrored image)
+        else:
+            x = Var(ops.nchw_to_nhwc(img_nchw))
         x = self.conv(ctx, x, "conv1", need_dx=False)
         x = self.bn_act(ctx, x, "bn1", relu=True)
         x = self.conv(ctx, x, "conv2")

@@ -24,7 +24,43 @@ logger = logging.getLogger(__name__)
 
 
 def _unwrap(model):
+    """The fused path drives the engine of the wrapped module directly, so wrappers cannot be silently bypassed:
+    nn.DataParallel over several devices would run the whole batch on one GPU -- refused (launch one process per GPU
+    instead); a 1-device DataParallel / DistributedDataParallel wrapper is transparent, and
+    the gradient all-reduce DDP would have done in its autograd hooks is done explicitly in _fused_step."""
+    if isinstance(model, torch.nn.DataParallel) and len(model.device_ids or []) > 1:
+        raise RuntimeError("fpd_b200: nn.DataParallel over %d devices is not supported by the fused path (it would use one "
+                           "GPU); run one process per GPU (torch.distributed.run), device_ids=[local_rank]"
+                           % len(model.device_ids))
     return model.module if hasattr(model, "module") else model
+
+
+def _loss_shape_ok(config_or_none, J, h, w):
+    """The fused FPD loss kernel (csrc/loss.cu) wants h*w % 64 == 0 and J <= 64; anything else takes the generic route."""
+    return (h * w) % 64 == 0 and 1 <= J <= 64
+
+
+_flat_grad_cache = {}
+
+
+def _allreduce_grads_(net, grads):
+    """One all-reduce (mean over ranks) of all parameter gradients, through one flat buffer (what DDP's bucketing does)."""
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    n = sum(g.numel() for g in grads)
+    key = (id(net), n)
+    flat = _flat_grad_cache.get(key)
+    if flat is None:
+        _flat_grad_cache.clear()
+        flat = _flat_grad_cache[key] = torch.empty(n, dtype=torch.float32, device=grads[0].device)
+    views, off = [], 0
+    for g in grads:
+        views.append(flat[off:off + g.numel()].view(g.shape))
+        off += g.numel()
+    torch._foreach_copy_(views, grads)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.mul_(1.0 / world)
+    return views
 
 
 def _is_fpd_net(model):
@@ -51,9 +87,18 @@ def _fused_step(model, tmodel, input, target, target_weight, alpha, use_tw):
     tw = target_weight.reshape(B, J) if use_tw else torch.ones(B, J, device=x.device)
     losses, grads = ops.fpd_loss(outs, target.contiguous().float(), t_last, tw.contiguous().float(), alpha)
     pg = eng.backward(ctx, grads)
-    for p in net.parameters():
+    params = [p for p in net.parameters() if p.requires_grad]      # frozen parameters keep whatever .grad they had
+    glist = []
+    for p in params:
         g = pg.get(p)
-        p.grad = torch.zeros_like(p) if g is None else g.reshape(p.shape)
+        glist.append(torch.zeros_like(p) if g is None else g.reshape(p.shape))
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        # one process per GPU: replicas stay identical only if every rank steps on the mean gradient
+        glist = _allreduce_grads_(net, glist)
+        glist = [g.clone() for g in glist]     # the flat buffer is reused next step; .grad must own its memory
+    for p, g in zip(params, glist):
+        p.grad = g
     return losses, outs[-1]
 
 
@@ -93,10 +138,14 @@ def train(config, train_loader, model, criterion, optimizer, epoch, output_dir, 
     model.train()
     fused = _is_fpd_net(model) and _is_fpd_criterion(criterion)
     end = time.time()
+    shape_checked = False
     for i, (input, target, target_weight, meta) in enumerate(train_loader):
         data_time.update(time.time() - end)
         target = target.cuda(non_blocking=True)
         target_weight = target_weight.cuda(non_blocking=True)
+        if fused and not shape_checked:
+            fused = _loss_shape_ok(config, target.shape[1], target.shape[2], target.shape[3])
+            shape_checked = True
         if fused:
             optimizer.zero_grad()
             l3, out_nhwc = _fused_step(model, None, input, target, target_weight, 0.0, criterion.use_target_weight)
@@ -139,10 +188,14 @@ def fpd_train(config, train_loader, model, tmodel, pose_criterion, kd_pose_crite
              and _is_fpd_criterion(kd_pose_criterion)
              and pose_criterion.use_target_weight == kd_pose_criterion.use_target_weight)
     end = time.time()
+    shape_checked = False
     for i, (input, target, target_weight, meta) in enumerate(train_loader):
         data_time.update(time.time() - end)
         target = target.cuda(non_blocking=True)
         target_weight = target_weight.cuda(non_blocking=True)
+        if fused and not shape_checked:
+            fused = _loss_shape_ok(config, target.shape[1], target.shape[2], target.shape[3])
+            shape_checked = True
         if fused:
             optimizer.zero_grad()
             l3, out_nhwc = _fused_step(model, tmodel, input, target, target_weight, alpha,

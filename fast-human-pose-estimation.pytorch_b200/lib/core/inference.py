@@ -32,15 +32,34 @@ def get_max_preds(batch_heatmaps):
     return preds_from_argmax(idx.cpu().numpy(), maxvals.cpu().numpy(), batch_heatmaps.shape[3])
 
 
+def _inverse_affine(center, scale, output_size):
+    """The 2x3 matrix the reference obtains from get_affine_transform(center, scale, 0, output_size, inv=1)
+    (lib/utils/transforms.py:57-89): three corresponding points -- centre, centre shifted up by half the box width, and
+    the perpendicular third point -- held in float32 exactly like the reference's `src` / `dst` arrays, then the 3-point
+    affine solved in float64 (what cv2.getAffineTransform does). Only scale[0] enters (the reference derives both axes
+    from the box width)."""
+    c = np.asarray(center, np.float32)
+    src_w = np.asarray(scale, np.float32)[0] * np.float32(200.0)
+    dst_w, dst_h = output_size[0], output_size[1]
+    src = np.zeros((3, 2), np.float32)
+    dst = np.zeros((3, 2), np.float32)
+    src[0] = c
+    src[1] = c + np.array([0.0, float(src_w * np.float32(-0.5))])
+    dst[0] = [dst_w * 0.5, dst_h * 0.5]
+    dst[1] = np.array([dst_w * 0.5, dst_h * 0.5]) + np.array([0, dst_w * -0.5], np.float32)
+    for p in (src, dst):
+        d = p[0] - p[1]
+        p[2] = p[1] + np.array([-d[1], d[0]], np.float32)
+    a = np.concatenate([dst.astype(np.float64), np.ones((3, 1))], 1)
+    return np.linalg.solve(a, src.astype(np.float64)).T          # maps heat-map (dst) coordinates to image (src)
+
+
 def transform_preds(coords, center, scale, output_size):
-    """Closed form of lib/utils/transforms.py:49-54 + :57-89 for rot = 0 (the only call the hot path makes):
-    the inverse affine is a uniform scale by (scale[0]*200 / output_w) about the heat-map centre plus the
-    translation to `center`."""
+    """lib/utils/transforms.py:49-54 for the whole [J,2] array at once (rot = 0 is the only call the hot path makes)."""
     coords = np.asarray(coords, dtype=np.float64)
-    s = float(scale[0]) * 200.0 / float(output_size[0])
+    t = _inverse_affine(center, scale, output_size)
     out = np.zeros(coords.shape)
-    out[:, 0] = (coords[:, 0] - output_size[0] * 0.5) * s + center[0]
-    out[:, 1] = (coords[:, 1] - output_size[1] * 0.5) * s + center[1]
+    out[:, 0:2] = coords[:, 0:2] @ t[:, :2].T + t[:, 2]
     return out
 
 

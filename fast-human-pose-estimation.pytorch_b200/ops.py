@@ -399,6 +399,14 @@ def nchw_to_nhwc(x, out=None):
     return y
 
 
+def nchw_to_nhwc_flipw(x, out=None):
+    """NHWC copy of the W-mirrored image (flip-test input, function.py:218-221) in the same single pass."""
+    B, C, H, W = x.shape
+    y = out if out is not None else torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
+    N.check(N.lib().fpd_nchw_to_nhwc_flipw(_p(x), _p(y), B, C, H, W, _stream()), "nchw_to_nhwc_flipw")
+    return y
+
+
 def nhwc_to_nchw(x, out=None):
     B, H, W, C = x.shape
     y = out if out is not None else torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)

@@ -10,7 +10,9 @@ import torch.distributed as dist
 
 
 def shard_range(global_batch, rank, world):
-    """Contiguous per-image shard [lo, hi) of a global batch (per-image data parallelism, no data-path collective)."""
+    """Contiguous per-image shard [lo, hi) of a global batch (per-image data parallelism, no data-path collective).
+    NB: allreduce_mean_ averages the per-rank gradients with equal weights, which equals the global-batch mean only for
+    EQUAL shards (the losses are per-rank batch means) -- keep global_batch a multiple of world for training."""
     per = global_batch // world
     rem = global_batch % world
     lo = rank * per + min(rank, rem)

@@ -78,6 +78,10 @@ class FPDTrainStep:
                          and os.environ.get("FPD_PIPELINE_TEACHER", "0") != "0")   # measured: no gain over the plain 2nd stream
         self.x_next = self.t_cur = self.t_next = None
         self._have_next = False
+        self._static_shapes = None
+        self._teacher_gen = 0
+        self.last_outs = None      # student heat-maps (NHWC, per stack) and the teacher's last stack of the latest step:
+        self.last_teacher = None   # kept referenced so the graph's memory pool never recycles them
         self._side = torch.cuda.Stream() if (teacher is not None and self.overlap_teacher) else None
         self._t_keep = None
         # weight gradients (leaves of the backward graph: they only feed the final gradient gather) on a third stream, so
@@ -145,6 +149,7 @@ class FPDTrainStep:
                 t_ctx = self.teacher.engine().forward(x, False, record_tape=False)
                 t_last = t_ctx.outs[-1].data
         outs = [v.data for v in ctx.outs]
+        self.last_outs, self.last_teacher = outs, t_last
         losses, grads = ops.fpd_loss(outs, target, t_last, tw, self.alpha, losses_out=self.losses)
         pg = s_eng.backward(ctx, grads, wgrad_stream=self._wstream)
         self._gather_grads(pg)
@@ -198,9 +203,17 @@ class FPDTrainStep:
         same batch as `x`. Without `next_x` the teacher for the following step is run up front (no overlap)."""
         tw = target_weight.reshape(target_weight.shape[0], -1)
         if self.use_graph:
+            shapes = (tuple(x.shape), tuple(target.shape), tuple(tw.shape))
+            t_gen = self.teacher.engine().generation if self.teacher is not None else 0
+            if self.graph is not None and (shapes != self._static_shapes or t_gen != self._teacher_gen):
+                # a short last batch / a different resolution, or teacher weights reloaded after capture (the graph holds
+                # pointers to the teacher's prepared weights): capture again instead of broadcasting or using stale data
+                self.graph = None
             if self.graph is None:
                 xd, td, wd = (t.cuda(non_blocking=True).float().contiguous() for t in (x, target, tw))
                 self._capture(xd, td, wd)
+                self._static_shapes = shapes
+                self._teacher_gen = self.teacher.engine().generation if self.teacher is not None else 0
                 self._have_next = False
             if self.pipeline:
                 if self._have_next:
@@ -236,4 +249,26 @@ class FPDTrainStep:
         self.step_count += 1
         ops.adam_flat(self.flat.flat, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0],
                       self.betas[1], self.eps, self.wd, self.step_count, grad_scale=gscale)
+        # weights and running statistics were just rewritten through raw pointers (and, in graph mode, without running any
+        # Python): drop the student's cached eval-mode operands so a following validation sees the new values
+        self.student.engine().invalidate_eval_cache()
         return losses
+
+    def invalidate(self):
+        """Force a re-capture on the next step (after editing teacher / student tensors in place by hand)."""
+        self.graph = None
+
+    # ------------------------------------------------------------------ checkpointing (the reference saves
+    # optimizer.state_dict() next to the model, lib/utils/utils.py:75-84 / tools/fpd_train.py:277-291)
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd,
+                "numel": self.flat.numel}
+
+    def load_state_dict(self, sd):
+        if int(sd["numel"]) != self.flat.numel:
+            raise ValueError("optimizer state is for %d flat parameters, this step has %d" % (sd["numel"], self.flat.numel))
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.lr, self.betas, self.eps, self.wd = sd["lr"], tuple(sd["betas"]), sd["eps"], sd["weight_decay"]

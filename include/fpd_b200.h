@@ -219,6 +219,9 @@ int fpd_upsample2x_add(const float* up1, const float* low, float* out, int B, in
                        fpd_stream_t stream); /* H,W = output size */
 int fpd_upsample2x_bwd(const float* dout, float* dlow, int B, int H, int W, int C, fpd_stream_t stream);
 int fpd_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, fpd_stream_t stream);
+/* Same, with the image mirrored along W on the way (the flipped input of the flip test, lib/core/function.py:218-221:
+ * np.flip(input, 3)), so the second forward needs no separate flip pass. */
+int fpd_nchw_to_nhwc_flipw(const float* x_nchw, float* y_nhwc, int B, int C, int H, int W, fpd_stream_t stream);
 int fpd_nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, fpd_stream_t stream);
 int fpd_add(const float* a, const float* b, float* out, int64_t n, fpd_stream_t stream);
 

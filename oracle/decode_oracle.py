@@ -191,7 +191,9 @@ def rescore(kpts, box_scores, in_vis_thre):
         ks, vn = 0.0, 0
         for t_s in kpts[i, :, 2]:            # sequential sum, like the reference loop
             if t_s > in_vis_thre:
-                ks, vn = ks + t_s, vn + 1
+                # float64 accumulation: `0 + np.float32` promoted to float64 under the numpy (< 2) the reference ran on;
+                # numpy >= 2 (NEP 50) would keep float32 here -- the golden vectors use float64 key points, where both agree
+                ks, vn = ks + float(t_s), vn + 1
         if vn != 0:
             ks = ks / vn
         out[i] = ks * box_scores[i]

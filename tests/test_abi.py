@@ -42,7 +42,8 @@ def test_every_host_module_imports_on_cpu():
     """Import (= byte-compile) every Python module of the package and the top-level scripts: no GPU needed."""
     import importlib
     import fpd_b200  # noqa: F401
-    for name in ("_native", "ops", "engine", "engine_hrnet", "autograd_bridge", "train_step", "parallel",
+    for name in ("_native", "ops", "engine", "engine_hrnet", "autograd_bridge", "train_step", "infer_step", "parallel",
+                 "dropin", "targets",
                  "lib.models.hourglass", "lib.models.pose_hrnet", "lib.core.loss", "lib.core.function",
                  "lib.core.inference", "lib.core.evaluate", "lib.utils.transforms", "lib.nms.nms"):
         importlib.import_module("fpd_b200." + name)
@@ -50,7 +51,7 @@ def test_every_host_module_imports_on_cpu():
     for script in ("bench.py", "__graft_entry__.py", "tools/profile_step.py", "tools/profile_kernel.py",
                    "tools/profile_convs.py", "tools/bench_conv_variants.py", "tools/diag_net.py", "tools/diag_grad.py",
                    "tools/summarize_profiles.py", "tools/diag_conv_h.py", "tools/diag_wgrad.py", "tools/diag_wgrad3.py",
-                   "tools/diag_wgrad_shift.py"):
+                   "tools/diag_wgrad_shift.py", "tools/timeline_step.py"):
         ast.parse(open(os.path.join(ROOT, script)).read(), script)
 
 
@@ -87,23 +88,29 @@ def test_kernel_shape_planners_on_cpu():
 
 
 def test_bench_reference_arm_contract_on_cpu(capsys):
-    """`bench.py --impl reference` (the oracle port of the FPD step on the host cores) prints one JSON line with the
-    contract's keys; runs here without a GPU (one short timed step)."""
+    """`bench.py --impl reference` (the reference's own modules from oracle/_ref on the host cores; oracle port when that
+    directory is absent) prints one JSON line with the contract's keys for every config; runs here without a GPU (one
+    short timed step at a reduced batch)."""
     import json
     import sys
     import types
     sys.path.insert(0, ROOT)
     import bench
+    from oracle import ref_modules as R
     os.environ["FPD_CPU_THREADS"] = str(min(8, len(os.sched_getaffinity(0))))
     try:
-        bench.run_reference(types.SimpleNamespace(steps=1, warmup=0, gpus=1), rank=0)
+        for name, B in (("hg_mse_s1", 2), ("hg_fpd", 1), ("hg_infer", 1)) + ((("hrnet_fpd", 1),) if R.available() else ()):
+            bench.run_reference(types.SimpleNamespace(steps=1, warmup=0, gpus=1, config=name, batch=B), rank=0)
+            line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+            assert line["impl"] == "reference" and line["metric"] == "images/sec" and line["unit"] == "images/s"
+            assert line["value"] > 0 and line["higher_is_better"] is True and line["n_gpus"] == 1
+            assert line["steps"] == 1 and line["warmup"] == 0
+            assert line["config"] == bench.workload_config(name, 1, B)          # the GPU arm's config keys
+            assert line["cpu_baseline"]["kind"] == ("reference" if R.available() else "port")
+            assert line["cpu_baseline"]["cores"] >= 1
+            assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     finally:
         os.environ.pop("FPD_CPU_THREADS", None)
-    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
-    assert line["impl"] == "reference" and line["metric"] == "images/sec" and line["unit"] == "images/s"
-    assert line["value"] > 0 and line["higher_is_better"] is True and line["n_gpus"] == 1
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
-    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     # other ranks of a torchrun launch stay silent
-    bench.run_reference(types.SimpleNamespace(steps=1, warmup=0, gpus=2), rank=1)
+    bench.run_reference(types.SimpleNamespace(steps=1, warmup=0, gpus=2, config="hg_fpd", batch=1), rank=1)
     assert capsys.readouterr().out == ""

@@ -191,3 +191,72 @@ def test_hrnet_dropin_state_dict_matches_reference_keys():
     net.load_state_dict(gold_sd, strict=True)
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         net(torch.zeros(1, 3, 64, 64))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# decode tail (tests/golden/decode2.npz: the reference's get_final_preds / accuracy / oks_nms / generate_target)
+# --------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def decode2():
+    return _load("decode2.npz")
+
+
+@pytest.mark.parametrize("tag", ["sq", "rect"])
+def test_oracle_final_preds_and_accuracy_match_reference_golden(decode2, tag):
+    z = decode2
+    for pp in (1, 0):
+        preds, maxvals = D.get_final_preds(bool(pp), z[tag + "/hm"].copy(), z[tag + "/center"], z[tag + "/scale"])
+        assert np.abs(preds - z["%s/preds_pp%d" % (tag, pp)]).max() < 1e-9
+        assert np.array_equal(maxvals, z["%s/maxvals_pp%d" % (tag, pp)])
+    acc, avg, cnt, pred = D.accuracy(z[tag + "/acc_out"], z[tag + "/acc_target"])
+    assert np.array_equal(acc, z[tag + "/acc"]) and avg == float(z[tag + "/avg_acc"]) and cnt == int(z[tag + "/cnt"])
+    assert np.array_equal(pred, z[tag + "/acc_pred"])
+
+
+def test_closed_form_transform_preds_matches_reference_golden(decode2):
+    """lib.core.inference.transform_preds restates the reference's float32 corner points + cv2's 3-point solve."""
+    import fpd_b200  # noqa: F401
+    from fpd_b200.lib.core.inference import transform_preds
+    z = decode2
+    for tag in ("sq", "rect"):
+        hm = z[tag + "/hm"]
+        coords, _ = D.get_max_preds(hm)
+        W, H = hm.shape[3], hm.shape[2]
+        for i in range(hm.shape[0]):
+            got = transform_preds(coords[i], z[tag + "/center"][i], z[tag + "/scale"][i], [W, H])
+            ref = z[tag + "/preds_pp0"][i]
+            # get_final_preds stores the result into the float32 `preds` array (inference.py:71-77): bit-exact after the cast
+            assert np.array_equal(got.astype(np.float32), ref), (tag, i, np.abs(got - ref).max())
+
+
+def test_oracle_oks_nms_and_rescore_match_reference_golden(decode2):
+    z = decode2
+    for tag in ("oks_a", "oks_b", "oks_c"):
+        r = D.rescore(z[tag + "/kpts"], z[tag + "/box_score"], float(z["oks/in_vis_thre"]))
+        assert np.array_equal(r, z[tag + "/rescored"])
+        assert D.oks_nms(z[tag + "/kpts"], z[tag + "/area"], r, float(z["oks/oks_thre"])) == list(z[tag + "/keep"])
+        assert D.oks_nms(z[tag + "/kpts"], z[tag + "/area"], r, 0.5, None, 0.3) == list(z[tag + "/keep_vis"])
+
+
+def test_oracle_generate_target_matches_reference_golden(decode2):
+    z = decode2
+    jw = np.array([1., 1., 1., 1., 1., 1., 1., 1.2, 1.2, 1.5, 1.5, 1., 1., 1.2, 1.2, 1.5, 1.5], np.float32).reshape(17, 1)
+    for tag, img, hm, w in (("tgt_sq", (256, 256), (64, 64), None), ("tgt_rect", (192, 256), (48, 64), jw)):
+        for i in range(z[tag + "/joints"].shape[0]):
+            t, tw = D.generate_target(z[tag + "/joints"][i], z[tag + "/joints_vis"][i], img, hm, 2, w)
+            assert np.array_equal(t, z[tag + "/target"][i]) and np.array_equal(tw, z[tag + "/target_weight"][i])
+
+
+def test_host_oks_helpers_match_reference_golden(decode2):
+    """lib.nms.nms.oks_iou / soft_oks_nms are host numpy in the drop-in too: same numbers as the oracle's oks_iou."""
+    import fpd_b200  # noqa: F401
+    from fpd_b200.lib.nms import nms as M
+    z = decode2
+    k = z["oks_a/kpts"].reshape(40, -1)
+    a = z["oks_a/area"]
+    got = M.oks_iou(k[3], k[4:], a[3], a[4:], None, 0.3)
+    ref = D.oks_iou(k[3], k[4:], a[3], a[4:], None, 0.3)
+    assert np.array_equal(got, ref)
+    db = [{"keypoints": z["oks_a/kpts"][i], "area": a[i], "score": z["oks_a/rescored"][i]} for i in range(40)]
+    keep = M.soft_oks_nms(db, 0.9)
+    assert len(keep) == 20 and keep[0] == int(np.argmax(z["oks_a/rescored"]))
