@@ -36,6 +36,10 @@ _SIGNATURES = {
     "fpd_conv2d_tc_h": (c_int, [P, P, P, P, c_int, P, P, c_int, P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int,
                                 c_int, P]),
     "fpd_conv2d_tc_h_set_profile_buffer": (c_int, [P]),
+    "fpd_conv2d_tc_h_stats_blocks": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "fpd_conv2d_tc_h_stats": (c_int, [P, P, P, P, c_int, P, P, c_int, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, P, P, P]),
+    "fpd_bn_finalize_sums": (c_int, [P, c_int, P, c_int64, c_int, P, P, c_float, c_float, P, P, P, P, P, P, P, P]),
     "fpd_channel_sum_fused": (c_int, [P, c_int64, c_int, c_float, P, P, P, c_size_t, P, P]),
     "fpd_bn_bwd_reduce_fused": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int, P, P, c_size_t, P, P]),
     "fpd_bn_stats_fused": (c_int, [P, c_int64, c_int, P, P, c_float, c_float, P, P, P, P, P, P, P, P, c_size_t, P, P]),
@@ -65,6 +69,7 @@ _SIGNATURES = {
     "fpd_channel_reduce_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "fpd_channel_sum": (c_int, [P, c_int64, c_int, c_float, P, P, c_size_t, P]),
     "fpd_bn_bwd_reduce": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int, P, P, c_size_t, P]),
+    "fpd_bn_bwd_apply_sum": (c_int, [P, P, P, P, P, P, P, c_int, P, P, P, P, c_int64, c_int, P, c_size_t, P]),
     "fpd_bn_bwd_apply": (c_int, [P, P, P, P, P, P, P, c_int, P, c_int, P, c_int64, c_int, P]),
     "fpd_affine_act_bwd": (c_int, [P, P, P, P, P, c_int, c_int, P, c_int64, c_int, P]),
     "fpd_maxpool2x2_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),

@@ -134,6 +134,26 @@ int fpd_conv2d_tc_h(const float* x, const float* pre_mean, const float* pre_scal
                           out_scale, in_scale, B, H, W, Cin, Cout, ksize, device_sm_count(), S(stream));
 }
 
+int fpd_conv2d_tc_h_stats_blocks(int B, int H, int W, int Cin, int Cout, int ksize, int f16) {
+  return conv_tc_h_stats_grid(B, H, W, Cin, Cout, ksize, f16, device_sm_count());
+}
+int fpd_conv2d_tc_h_stats(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
+                          int pre_relu, const void* w_hi, const void* w_lo, int f16, const float* bias,
+                          const float* residual, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
+                          int ksize, double* stat_part, const float* stat_pivot, fpd_stream_t stream) {
+  FPD_REQUIRE(stat_part != nullptr, "fpd_conv2d_tc_h_stats: stat_part is NULL (use fpd_conv2d_tc_h)");
+  return conv_tc_h_launch(x, pre_mean, pre_scale, pre_shift, pre_relu, w_hi, w_lo, f16, bias, residual, nullptr, y,
+                          out_scale, nullptr, B, H, W, Cin, Cout, ksize, device_sm_count(), S(stream), stat_part,
+                          stat_pivot);
+}
+int fpd_bn_finalize_sums(const double* part, int nblocks, const float* pivot, int64_t P, int C, const float* gamma,
+                         const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                         float* mean, float* var_biased, float* scale, float* shift, float* invstd,
+                         fpd_stream_t stream) {
+  return bn_finalize_sums(part, nblocks, pivot, P, C, gamma, beta, eps, momentum, running_mean, running_var, mean,
+                          var_biased, scale, shift, invstd, S(stream));
+}
+
 int fpd_channel_sum_fused(const float* dy, int64_t P, int C, float scale, float* out, float* amax_scale,
                           void* workspace, size_t workspace_bytes, unsigned int* counter, fpd_stream_t stream) {
   return channel_sum_fused(dy, P, C, scale, out, amax_scale, workspace, workspace_bytes, counter, S(stream));
@@ -258,6 +278,12 @@ int fpd_bn_bwd_reduce(const float* da, const float* x, const float* mean, const 
                       const float* shift, int relu, int64_t P, int C, float* sums, void* ws, size_t wsb,
                       fpd_stream_t stream) {
   return bn_bwd_reduce(da, x, mean, invstd, scale, shift, relu, P, C, sums, ws, wsb, S(stream));
+}
+int fpd_bn_bwd_apply_sum(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
+                         const float* shift, const float* gamma, int relu, const float* sums, float* dx, float* dx_sum,
+                         float* amax_scale, int64_t P, int C, void* ws, size_t wsb, fpd_stream_t stream) {
+  return bn_bwd_apply_sum(da, x, mean, invstd, scale, shift, gamma, relu, sums, dx, dx_sum, amax_scale, P, C, ws, wsb,
+                          S(stream));
 }
 int fpd_bn_bwd_apply(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
                      const float* shift, const float* gamma, int relu, const float* sums, int accumulate, float* dx,

@@ -322,7 +322,12 @@ int conv_simt_wgrad(const float* x, const float* dy, float* dw_oihw, float scale
   FPD_REQUIRE(workspace && ws_bytes >= g.bytes, "conv_simt_wgrad: workspace too small (%zu < %zu)", ws_bytes, g.bytes);
   const int CoutP8 = (Cout + 7) & ~7;
   const size_t smem = (size_t)kSub * CoutP8 * sizeof(float);
-  FPD_REQUIRE(smem <= 48 * 1024, "conv_simt_wgrad: Cout=%d too wide for the CUDA-core path", Cout);
+  FPD_REQUIRE(smem <= 192 * 1024, "conv_simt_wgrad: Cout=%d too wide for the CUDA-core path", Cout);
+  static bool wattr = false;
+  if (!wattr) {   // dy sub-chunk tile [64][Cout]: opt in beyond 48 KB for the wide HRNet stride-2 convs (Cout 256 / 384)
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024));
+    wattr = true;
+  }
   conv_wgrad_partial_kernel<<<g.nchunks, 256, smem, stream>>>(x, dy, (float*)workspace, B, H, W, Cin, Cout, k, stride,
                                                               pad, Ho, Wo, g.chunk);
   FPD_LAUNCH_CHECK();

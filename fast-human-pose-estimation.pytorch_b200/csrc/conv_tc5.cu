@@ -73,6 +73,9 @@ struct ConvHParams {
   float out_scale;
   const float* in_scale;   // nullable device float[2] {S, 1/S}: operands are x * S, the epilogue multiplies by 1/S (exact
                            // powers of two; puts small-magnitude gradients into the fp16 range, see channel_sum amax)
+  double* stat_part;        // kStats: per-CTA column sums of the OUTPUT, [gridDim.x][Cout][2] = {sum (y - pivot), sum (y - pivot)^2}
+  const float* stat_pivot;  // nullable [Cout]: per-channel pivot (any value near the channel mean; zero if null)
+  int stat_bytes;           // shared-memory bytes of the per-warp accumulators (4 x Cout x 16), 0 without statistics
   long long* prof;   // optional per-CTA stall counters [grid][16] (fpd_conv2d_tc_h_set_profile_buffer); null normally
   int dbg;   // timing ablations only (FPD_CONV_DBG bit mask, tools/diag_conv_h.py): 1 no MMA, 2 no weight TMA, 4 no x TMA,
              // 8 no transform/copy work, 16 no epilogue global traffic, 32 no halo split. Results are garbage when set.
@@ -173,7 +176,14 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvHParams& p, int tile) 
   return t;
 }
 
-template <bool kF16>
+// kStats: the epilogue also accumulates, per output channel, the sums the next train-mode BatchNorm needs (nn.BatchNorm2d
+// batch statistics of this tensor, hourglass.py:18-26) -- the separate statistics pass over the tensor (bn_stats_partial,
+// one more HBM read per BatchNorm) disappears. Per lane: fp32 sums over its 8 rows of (y - pivot) and (y - pivot)^2
+// (8-term sums: as tight as the pivoted 14-row runs of bn_stats_partial_kernel), then fp64: shuffle tree over the 4 lanes
+// sharing a column, per-WARP shared-memory accumulators (no atomics: deterministic), fixed-order merge of the 4 warps
+// at the end, one [Cout][2] block of partial sums per CTA; bn_sums_finalize_kernel (elementwise.cu) merges the CTAs.
+// A separate instantiation: the plain kernel's code is unchanged.
+template <bool kF16, bool kStats>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w_hi,
                  const __grid_constant__ CUtensorMap tm_w_lo, const ConvHParams p) {
@@ -200,6 +210,7 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   float* s_mean = reinterpret_cast<float*>(tail + 1024);
   float* s_scale = s_mean + kParamFloats;
   float* s_shift = s_scale + kParamFloats;
+  double* s_stat = reinterpret_cast<double*>(tail + kTailBytes);   // kStats: [4 epilogue warps][Cout][2]
 
   // warp index made provably warp-uniform (shfl broadcast): the single-thread TMA / MMA issue code below then keeps its
   // descriptors in uniform registers. With a threadIdx-derived `if (lane == 0)` around the whole role ptxas wraps every
@@ -399,6 +410,11 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const bool prof = p.prof != nullptr;
     long long c_tfull = 0;
     const long long c_start = prof ? clock64() : 0;
+    double* my_stat = s_stat + (size_t)q * p.Cout * 2;   // this warp's accumulators
+    if (kStats) {
+      for (int i = lane; i < p.Cout * 2; i += 32) my_stat[i] = 0.0;
+      __syncwarp();
+    }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
       const uint32_t acs = p.acc_stages == 2 ? (tile_iter & 1) : 0u;
       const uint32_t acph = (p.acc_stages == 2 ? (tile_iter >> 1) : tile_iter) & 1;
@@ -474,9 +490,12 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           }
         }
         __syncwarp();
+        float ps1[4] = {0.f, 0.f, 0.f, 0.f}, ps2[4] = {0.f, 0.f, 0.f, 0.f};   // kStats: this lane's 8-row sums
         if (act) {
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + t.n0w + col));
+          float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kStats && p.stat_pivot) pv = __ldg(reinterpret_cast<const float4*>(p.stat_pivot + t.n0w + col));
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rl = it * 4 + sub;
@@ -493,6 +512,27 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 o.z = k.z > 0.f ? o.z : 0.f; o.w = k.w > 0.f ? o.w : 0.f;
               }
               *reinterpret_cast<float4*>(p.y + off) = o;
+              if (kStats) {
+                const float d0 = o.x - pv.x, d1 = o.y - pv.y, d2 = o.z - pv.z, d3 = o.w - pv.w;
+                ps1[0] += d0; ps1[1] += d1; ps1[2] += d2; ps1[3] += d3;
+                ps2[0] = fmaf(d0, d0, ps2[0]); ps2[1] = fmaf(d1, d1, ps2[1]);
+                ps2[2] = fmaf(d2, d2, ps2[2]); ps2[3] = fmaf(d3, d3, ps2[3]);
+              }
+            }
+          }
+        }
+        if (kStats) {
+          // fp64 from here on: sum over the 4 lanes (sub = 0..3) that hold the same 4 columns, then into this warp's
+          // accumulators (lanes 0..7 own 4 distinct columns each: no conflicts, no atomics)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            double a = (double)ps1[j], b = (double)ps2[j];
+            a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
+            a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
+            if (sub == 0 && act) {
+              double* dst = my_stat + (size_t)(t.n0w + col + j) * 2;
+              dst[0] += a;
+              dst[1] += b;
             }
           }
         }
@@ -500,6 +540,16 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       }
       tc_fence_before_sync();
       warp_arrive(&tmem_empty[acs], lane);
+    }
+    if (kStats) {
+      // merge the four warps in a fixed order and publish this CTA's partial sums
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      const int et = q * 32 + lane;
+      for (int i = et; i < p.Cout * 2; i += 128) {
+        const double v = ((s_stat[i] + s_stat[(size_t)p.Cout * 2 + i]) + s_stat[(size_t)p.Cout * 4 + i]) +
+                         s_stat[(size_t)p.Cout * 6 + i];
+        p.stat_part[(size_t)blockIdx.x * p.Cout * 2 + i] = v;
+      }
     }
     if (prof && warp == 2 && lane == 0) {
       long long* o = p.prof + (size_t)blockIdx.x * 16;
@@ -725,7 +775,12 @@ int pow2_floor_div(int x, int cap) {
 int align1024(int x) { return (x + 1023) / 1024 * 1024; }
 
 // Fills the geometry / ring sizes; returns false if the shape does not fit.
-bool plan(ConvHParams& p, int B, int H, int W, int Cin, int Cout, int ksize, int f16, int passes) {
+bool plan(ConvHParams& p, int B, int H, int W, int Cin, int Cout, int ksize, int f16, int passes, int stats = 0) {
+  p.stat_bytes = 0;
+  if (stats) {
+    if (Cout > 256) return false;
+    p.stat_bytes = 4 * Cout * 16;
+  }
   const int cbch = f16 ? 64 : 32;
   if (!(ksize == 1 || ksize == 3)) return false;
   if (Cin < 4 || Cin > kMaxCinH || Cin % (f16 ? 8 : 4) != 0) return false;
@@ -759,7 +814,7 @@ bool plan(ConvHParams& p, int B, int H, int W, int Cin, int Cout, int ksize, int
   if (p.a_stages < 2) return false;
   p.w_tile_bytes = nt * 128;
   p.w_stage_bytes = (passes == 3 ? 2 : 1) * p.w_tile_bytes;
-  const int budget = 227 * 1024 - 1024 - kTailBytes - kEpiBytes;
+  const int budget = 227 * 1024 - 1024 - kTailBytes - kEpiBytes - p.stat_bytes;
   const int boxes = f16 ? 2 : 1;
   if (ksize == 3) {
     p.halo_w = p.bw + 2; p.halo_h = p.bh + 2;
@@ -809,17 +864,27 @@ bool conv_tc_h_supported(int Cin, int Cout, int ksize, int H, int W, int f16) {
   return plan(p, 1, H, W, Cin, Cout, ksize, f16, 3);
 }
 
+int conv_tc_h_stats_grid(int B, int H, int W, int Cin, int Cout, int ksize, int f16, int num_sms) {
+  ConvHParams p{};
+  if (!plan(p, B, H, W, Cin, Cout, ksize, f16, 3, 1)) return 0;
+  return p.num_tiles < num_sms ? p.num_tiles : num_sms;
+}
+
 int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                      int pre_relu, const void* w_hi, const void* w_lo, int f16, const float* bias,
                      const float* residual, const float* relu_mask, float* y, float out_scale, const float* in_scale,
-                     int B, int H, int W, int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream) {
+                     int B, int H, int W, int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream,
+                     double* stat_part, const float* stat_pivot) {
   FPD_REQUIRE(x && w_hi && y, "conv_tc_h: null operand");
   FPD_REQUIRE((double)B * H * W * Cout < 4294967296.0, "conv_tc_h: output has 2^32 or more elements");
   FPD_REQUIRE((pre_scale == nullptr) == (pre_shift == nullptr), "conv_tc_h: pre_scale/pre_shift come in pairs");
   FPD_REQUIRE(pre_scale != nullptr || pre_mean == nullptr, "conv_tc_h: pre_mean needs pre_scale/pre_shift");
   ConvHParams p{};
-  FPD_REQUIRE(plan(p, B, H, W, Cin, Cout, ksize, f16, w_lo ? 3 : 1),
-              "conv_tc_h: unsupported shape Cin=%d Cout=%d k=%d H=%d W=%d f16=%d", Cin, Cout, ksize, H, W, f16);
+  FPD_REQUIRE(plan(p, B, H, W, Cin, Cout, ksize, f16, w_lo ? 3 : 1, stat_part ? 1 : 0),
+              "conv_tc_h: unsupported shape Cin=%d Cout=%d k=%d H=%d W=%d f16=%d stats=%d", Cin, Cout, ksize, H, W, f16,
+              stat_part ? 1 : 0);
+  p.stat_part = stat_part;
+  p.stat_pivot = stat_pivot;
   p.pre_mean = pre_mean; p.pre_scale = pre_scale; p.pre_shift = pre_shift; p.pre_relu = pre_relu;
   p.bias = bias; p.residual = residual; p.relu_mask = relu_mask; p.y = y;
   p.out_scale = f16 ? out_scale * (1.0f / (float)(1 << kF16WeightScaleLog2)) : out_scale;
@@ -830,7 +895,7 @@ int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_sca
   p.prof = g_prof_buf;
   p.in_scale = in_scale;
   const size_t smem_bytes = (size_t)p.raw_stages * p.raw_stage_bytes + p.split_bytes +
-                            (size_t)p.w_stages * p.w_stage_bytes + kEpiBytes + kTailBytes + 1024;
+                            (size_t)p.w_stages * p.w_stage_bytes + kEpiBytes + kTailBytes + p.stat_bytes + 1024;
   FPD_REQUIRE(smem_bytes <= 227 * 1024, "conv_tc_h: shared memory plan %zu B too large", smem_bytes);
 
   CUtensorMap tm_x, tm_w_hi, tm_w_lo;
@@ -854,13 +919,18 @@ int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_sca
   }
   static bool attr_set = false;
   if (!attr_set) {
-    FPD_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    FPD_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_h_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_h_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_h_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_h_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_h_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  if (f16) conv_tc_h_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w_hi, tm_w_lo, p);
-  else conv_tc_h_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w_hi, tm_w_lo, p);
+  if (stat_part) {
+    if (f16) conv_tc_h_kernel<true, true><<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w_hi, tm_w_lo, p);
+    else conv_tc_h_kernel<false, true><<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w_hi, tm_w_lo, p);
+  } else if (f16) conv_tc_h_kernel<true, false><<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w_hi, tm_w_lo, p);
+  else conv_tc_h_kernel<false, false><<<grid, kThreads, smem_bytes, stream>>>(tm_x, tm_w_hi, tm_w_lo, p);
   FPD_LAUNCH_CHECK();
   return FPD_OK;
 }

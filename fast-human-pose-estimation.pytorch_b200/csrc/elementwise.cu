@@ -266,6 +266,43 @@ bn_stats_final_finalize_kernel(const double* __restrict__ part, int nblocks, int
   }
 }
 
+// BatchNorm finalize from per-CTA column SUMS written by a producing kernel's epilogue (conv_tc_h_kernel<.., kStats>:
+// part[b][c] = {sum (y - pivot_c), sum (y - pivot_c)^2} over the pixels CTA b wrote): mean = pivot + S1 / P,
+// var = S2 / P - (S1 / P)^2, all in fp64, CTAs merged in a fixed order (one warp per channel: lane-strided partial sums,
+// then the shuffle tree). Then exactly the finalize of bn_stats_final_finalize_kernel.
+__global__ void __launch_bounds__(256)
+bn_sums_finalize_kernel(const double* __restrict__ part, int nblocks, const float* __restrict__ pivot, int64_t P, int C,
+                        BnFinalize fz) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = lane; b < nblocks; b += 32) {
+    s1 += part[((size_t)b * C + c) * 2 + 0];
+    s2 += part[((size_t)b * C + c) * 2 + 1];
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane != 0) return;
+  const double inv = 1.0 / (double)P;
+  const double dm = s1 * inv;
+  double vv = s2 * inv - dm * dm;
+  if (vv < 0.0) vv = 0.0;
+  const float m = (float)((pivot ? (double)pivot[c] : 0.0) + dm), v = (float)vv;
+  fz.mean[c] = m;
+  fz.var[c] = v;
+  const float invstd = (float)(1.0 / sqrt((double)v + (double)fz.eps));
+  const float g = fz.gamma ? fz.gamma[c] : 1.f, b = fz.beta ? fz.beta[c] : 0.f;
+  fz.scale[c] = g * invstd;
+  fz.shift[c] = b;   // centred form: y = (x - mean) * scale + shift
+  if (fz.invstd) fz.invstd[c] = invstd;
+  if (fz.rmean) {
+    fz.rmean[c] = (1.f - fz.momentum) * fz.rmean[c] + fz.momentum * m;
+    const float unbiased = P > 1 ? v * ((float)P / (float)(P - 1)) : v;
+    fz.rvar[c] = (1.f - fz.momentum) * fz.rvar[c] + fz.momentum * unbiased;
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // generic per-channel sum reductions (NV sums per element), deterministic two-stage
 // -------------------------------------------------------------------------------------------------
@@ -430,6 +467,37 @@ struct BnBwdFunctor {
       v[0][j] = dz;
       v[1][j] = dz * ((xe[j] - me[j]) * ie[j]);
     }
+  }
+};
+
+// BatchNorm-backward apply that ALSO reduces its own output: dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) is
+// written and, in the same pass, summed per channel (= the bias gradient of the convolution that produced x) with its
+// max |dx| (= the power-of-two operand scale of that convolution's 3xFP16 data gradient). Replaces bn_bwd_apply +
+// channel_sum (one read of dx less, one partial-reduction launch less per conv whose output feeds exactly one BN).
+struct BnBwdApplySumFunctor {
+  const float* da; const float* x; const float* mean; const float* invstd; const float* scale; const float* shift;
+  const float* gamma; const float* sums; float* dx; int relu; int C; float inv_count;
+  __device__ void operator()(int64_t r, int cx, float (&v)[1][4]) const {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(da + r * C) + cx);
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + r * C) + cx);
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + cx);
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + cx);
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cx);
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cx);
+    const float4 gm = gamma ? __ldg(reinterpret_cast<const float4*>(gamma) + cx) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sums) + cx);
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(sums + C) + cx);
+    const float ge[4] = {g.x, g.y, g.z, g.w}, xe[4] = {xv.x, xv.y, xv.z, xv.w}, me[4] = {m.x, m.y, m.z, m.w},
+                ie[4] = {is.x, is.y, is.z, is.w}, se[4] = {sc.x, sc.y, sc.z, sc.w}, he[4] = {sh.x, sh.y, sh.z, sh.w},
+                ga[4] = {gm.x, gm.y, gm.z, gm.w}, a0[4] = {s0.x, s0.y, s0.z, s0.w}, a1[4] = {s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // same expression as bn_bwd_apply_kernel: bit-identical dx
+      const bool on = !relu || (fmaf(xe[j] - me[j], se[j], he[j]) > 0.f);
+      const float dz = on ? ge[j] : 0.f;
+      const float xh = (xe[j] - me[j]) * ie[j];
+      v[0][j] = ga[j] * ie[j] * (dz - a0[j] * inv_count - xh * a1[j] * inv_count);
+    }
+    *(reinterpret_cast<float4*>(dx + r * C) + cx) = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);
   }
 };
 
@@ -1075,6 +1143,17 @@ int bn_stats_fused(const float* x, int64_t P, int C, const float* gamma, const f
   return FPD_OK;
 }
 
+int bn_finalize_sums(const double* part, int nblocks, const float* pivot, int64_t P, int C, const float* gamma,
+                     const float* beta, float eps, float momentum, float* rmean, float* rvar, float* mean, float* var,
+                     float* scale, float* shift, float* invstd, cudaStream_t stream) {
+  FPD_REQUIRE(part && nblocks > 0 && P > 0 && C > 0 && mean && var && scale && shift, "bn_finalize_sums: bad argument");
+  FPD_REQUIRE((rmean == nullptr) == (rvar == nullptr), "bn_finalize_sums: running stats come in pairs");
+  BnFinalize fz{gamma, beta, eps, momentum, mean, var, scale, shift, invstd, rmean, rvar};
+  bn_sums_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, stream>>>(part, nblocks, pivot, P, C, fz);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
 int bn_bwd_reduce(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
                   const float* shift, int relu, int64_t P, int C, float* sums, void* workspace, size_t ws_bytes,
                   cudaStream_t stream) {
@@ -1092,6 +1171,14 @@ int bn_bwd_apply(const float* da, const float* x, const float* mean, const float
                                                              (float4*)dx, n4, C / 4, 1.f / (float)P);
   FPD_LAUNCH_CHECK();
   return FPD_OK;
+}
+
+int bn_bwd_apply_sum(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
+                     const float* shift, const float* gamma, int relu, const float* sums, float* dx, float* dx_sum,
+                     float* amax_scale, int64_t P, int C, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  FPD_REQUIRE(da && x && mean && invstd && scale && shift && sums && dx && dx_sum, "bn_bwd_apply_sum: null pointer");
+  BnBwdApplySumFunctor f{da, x, mean, invstd, scale, shift, gamma, sums, dx, relu, C, 1.f / (float)P};
+  return run_channel_reduce_fused<1>(f, P, C, 1.f, dx_sum, amax_scale, workspace, ws_bytes, nullptr, stream);
 }
 
 int affine_act_bwd(const float* da, const float* x, const float* mean, const float* scale, const float* shift,

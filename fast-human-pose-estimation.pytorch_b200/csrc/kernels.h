@@ -42,7 +42,11 @@ void conv_tc_h_set_profile_buffer(long long* buf);   // per-CTA stall counters [
 int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                      int pre_relu, const void* w_hi, const void* w_lo, int f16, const float* bias,
                      const float* residual, const float* relu_mask, float* y, float out_scale, const float* in_scale,
-                     int B, int H, int W, int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream);
+                     int B, int H, int W, int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream,
+                     double* stat_part = nullptr, const float* stat_pivot = nullptr);
+// BatchNorm statistics of the OUTPUT from the epilogue: number of per-CTA partial blocks the launch writes to
+// stat_part[blocks][Cout][2] (0: this shape cannot carry the statistics, e.g. Cout > 256)
+int conv_tc_h_stats_grid(int B, int H, int W, int Cin, int Cout, int ksize, int f16, int num_sms);
 
 // ---- wgrad_tc.cu : tcgen05 weight-gradient GEMM (K = pixels) ----
 bool wgrad_tc_supported(int Cin, int Cout, int ksize);
@@ -122,6 +126,11 @@ int bn_bwd_reduce(const float* da, const float* x, const float* mean, const floa
                   const float* shift, int relu, int64_t P, int C, float* sums, void* workspace, size_t ws_bytes,
                   cudaStream_t stream);
 // phase 2: dx (=|+=) gamma*invstd*(dz - sum_dz/P - xhat*sum_dzx/P); also writes dgamma = sum_dzx, dbeta = sum_dz
+// bn_bwd_apply + per-channel sum of dx (-> dx_sum[C]) + power-of-two operand scale of dx (-> amax_scale[2], nullable);
+// workspace as channel reduce
+int bn_bwd_apply_sum(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
+                     const float* shift, const float* gamma, int relu, const float* sums, float* dx, float* dx_sum,
+                     float* amax_scale, int64_t P, int C, void* workspace, size_t ws_bytes, cudaStream_t stream);
 int bn_bwd_apply(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
                  const float* shift, const float* gamma, int relu, const float* sums, int accumulate, float* dx,
                  int64_t P, int C, cudaStream_t stream);
@@ -146,6 +155,10 @@ int bn_bwd_reduce_fused(const float* da, const float* x, const float* mean, cons
                         const float* shift, int relu, int64_t P, int C, float* sums, void* workspace, size_t ws_bytes,
                         unsigned int* counter, cudaStream_t stream);
 // batch statistics + BatchNorm finalize (affine for the consumers, running-stat update) in one launch
+// finalize from per-CTA column sums {sum (y - pivot), sum (y - pivot)^2} (conv_tc_h epilogue statistics)
+int bn_finalize_sums(const double* part, int nblocks, const float* pivot, int64_t P, int C, const float* gamma,
+                     const float* beta, float eps, float momentum, float* rmean, float* rvar, float* mean, float* var,
+                     float* scale, float* shift, float* invstd, cudaStream_t stream);
 int bn_stats_fused(const float* x, int64_t P, int C, const float* gamma, const float* beta, float eps, float momentum,
                    float* rmean, float* rvar, float* mean, float* var, float* scale, float* shift, float* invstd,
                    void* workspace, size_t ws_bytes, unsigned int* counter, cudaStream_t stream);

@@ -23,6 +23,8 @@ FUSED_DGRAD = _FUSED in ("1", "all", "bwd", "dgrad")
 FUSED_WGRAD = _FUSED in ("1", "all", "bwd", "wgrad")
 # forward: run each hourglass level's skip branch on a side stream (see Engine.hourglass)
 FORK_UP1 = os.environ.get("FPD_FORK_UP1", "1") != "0"
+# opt-in SyncBN over the default process group (see parallel.py); the reference's semantics are per-replica statistics
+BN_SYNC = os.environ.get("FPD_BN_SYNC", "0") != "0"
 
 
 def precision_passes():
@@ -37,15 +39,18 @@ def precision_passes():
 
 class Var:
     """An activation tensor (NHWC) plus its gradient slot and cached batch statistics."""
-    __slots__ = ("data", "grad", "owned", "stats")
+    __slots__ = ("data", "grad", "owned", "stats", "stat_sums", "grad_sum")
 
     def __init__(self, data):
         self.data = data
         self.grad = None
         self.owned = False   # True if self.grad may be modified in place
         self.stats = None    # (mean, var) of data over pixels, shared by every BN that consumes it
+        self.stat_sums = None  # (part[nblocks,C,2] fp64, nblocks, pivot): column sums of data from the producing conv's epilogue
+        self.grad_sum = None   # (per-channel sum of grad, operand scale of grad) when grad came whole out of ONE kernel
 
     def add_grad(self, g, owned):
+        self.grad_sum = None      # whatever was known about the previous gradient is stale now
         if self.grad is None:
             self.grad, self.owned = g, owned
         elif self.owned:
@@ -60,6 +65,7 @@ class Var:
 
     def set_or_merge(self, dx, accumulated):
         if accumulated:
+            self.grad_sum = None
             return
         self.add_grad(dx, True)
 
@@ -180,6 +186,7 @@ class Engine:
                 self.bns[name] = BNRef(name, m)
         self._eval_cache = None
         self._eval_cache_key = None
+        self.bn_sync_group = None  # set to a process group (or True = default group) for SyncBN; FPD_BN_SYNC=1 does it globally
         self._generation = 0       # bumped by everything that writes parameters / buffers behind torch's back
         self._branch_streams = {}
         # load_state_dict() copies in place (bumps ._version, caught by _param_version) -- but a CUDA graph that baked the
@@ -232,7 +239,23 @@ class Engine:
             count = x.data.numel() // x.data.shape[-1]
             momentum = m.momentum if m.momentum is not None else 0.1
             track = m.track_running_stats and m.running_mean is not None
-            if x.stats is None and ops.FUSED_REDUCE and x.data.shape[-1] % 4 == 0:
+            if ctx.sync is not None:
+                # SyncBN: local statistics -> one small all-gather -> statistics of the global batch (parallel.py)
+                from . import parallel
+                if x.stats is None:
+                    x.stats = parallel.merge_bn_stats(*ops.bn_stats(x.data), group=ctx.sync[0])
+                mean, var = x.stats
+                scale, shift, invstd = ops.bn_finalize(mean, var, m.weight.detach(), m.bias.detach(), m.eps,
+                                                       count * ctx.sync[1], m.running_mean if track else None,
+                                                       m.running_var if track else None, momentum)
+            elif x.stats is None and x.stat_sums is not None:
+                # the producing convolution's epilogue already summed this tensor per channel: finalize only (no pass over x)
+                part, nblocks, pivot = x.stat_sums
+                mean, var, scale, shift, invstd = ops.bn_finalize_sums(
+                    part, nblocks, pivot, count, m.weight.detach(), m.bias.detach(), m.eps,
+                    m.running_mean if track else None, m.running_var if track else None, momentum)
+                x.stats = (mean, var)
+            elif x.stats is None and ops.FUSED_REDUCE and x.data.shape[-1] % 4 == 0:
                 # statistics + this BN's finalize in one launch
                 mean, var, scale, shift, invstd = ops.bn_stats_finalize(
                     x.data, m.weight.detach(), m.bias.detach(), m.eps, m.running_mean if track else None,
@@ -257,10 +280,18 @@ class Engine:
         scale, shift, mean, invstd, batch = aff
         tgt = x.accum_target()
         if batch:
-            dx, dgamma, dbeta = ops.bn_bwd(da, x.data, mean, invstd, scale, shift, m.weight.detach(), relu,
-                                           accumulate_into=tgt)
+            sync_mean = None
+            if ctx.sync is not None:
+                from . import parallel
+                sync_mean = lambda sums: parallel.allreduce_avg(sums, ctx.sync[0])     # noqa: E731
+            dx, dgamma, dbeta, dsum = ops.bn_bwd(da, x.data, mean, invstd, scale, shift, m.weight.detach(), relu,
+                                                 accumulate_into=tgt, sync_mean=sync_mean, want_dx_sum=True)
             ctx.pgrads[m.weight] = dgamma
             ctx.pgrads[m.bias] = dbeta
+            x.set_or_merge(dx, tgt is not None)
+            if dsum is not None and x.grad is dx:
+                x.grad_sum = dsum     # x.grad is exactly this kernel's output (until someone adds to it)
+            return
         else:  # eval-mode affine: statistics are constants, so no batch-statistics terms in dx
             sums = ops.bn_bwd_reduce(da, x.data, mean, invstd, scale, shift, relu)
             C = x.data.shape[-1]
@@ -281,8 +312,10 @@ class Engine:
             ctx.tape.append(bwd)
         return out
 
-    def conv(self, ctx, x, conv_name, bn_name=None, relu=False, residual=None, need_dx=True):
-        """y = conv(act(bn(x))) + bias (+ residual).  bn_name None -> the conv consumes x raw."""
+    def conv(self, ctx, x, conv_name, bn_name=None, relu=False, residual=None, need_dx=True, out_bn=None):
+        """y = conv(act(bn(x))) + bias (+ residual).  bn_name None -> the conv consumes x raw.
+        out_bn: name of a train-mode BatchNorm that will consume y (True: some BatchNorm, name unknown) -- the conv then
+        also emits y's per-channel sums from its epilogue (Var.stat_sums), pivoted on that module's running mean."""
         c = self.convs[conv_name]
         split = ctx.passes == 3
         scale = shift = mean = None
@@ -325,7 +358,19 @@ class Engine:
         if c.tc_fwd:
             w_hi, w_lo, use_h = ctx.weights.fwd(c, x.data.shape[1], x.data.shape[2],
                                                 also_dgrad=ctx.tape is not None and need_dx)
-            if FUSED_FWD:
+            stat_sums = None
+            if FUSED_FWD and use_h and out_bn and ctx.training and ctx.sync is None:
+                Bn, Hn, Wn = x.data.shape[0], x.data.shape[1], x.data.shape[2]
+                nblk = ops.conv2d_tc_h_stats_blocks(Bn, Hn, Wn, c.cin, c.cout, c.k, w_hi.dtype == torch.float16)
+                if nblk > 0:
+                    pivot = None
+                    if out_bn is not True and self.bns[out_bn].mod.running_mean is not None:
+                        pivot = self.bns[out_bn].mod.running_mean
+                    stat_sums = (torch.empty((nblk, c.cout, 2), dtype=torch.float64, device=x.data.device), nblk, pivot)
+            if stat_sums is not None:
+                y = ops.conv2d_tc_h(x.data, w_hi, w_lo, c.k, mean=mean, scale=scale, shift=shift, relu=relu, bias=bias,
+                                    residual=res, stats_part=stat_sums[0], stats_pivot=stat_sums[2])
+            elif FUSED_FWD:
                 # BN-apply + ReLU + operand split happen inside the conv kernel (no separate HBM pass)
                 conv_fn = ops.conv2d_tc_h if use_h else ops.conv2d_tc_fused
                 y = conv_fn(x.data, w_hi, w_lo, c.k, mean=mean, scale=scale, shift=shift, relu=relu, bias=bias,
@@ -337,6 +382,8 @@ class Engine:
             a = ops.affine_act(x.data, scale, shift, relu, mean=mean) if bn_name is not None else x.data
             y = ops.conv2d_simt_fwd(a, c.weight.detach(), bias=bias, residual=res, stride=c.stride, pad=c.pad)
         out = Var(y)
+        if c.tc_fwd:
+            out.stat_sums = stat_sums
         if ctx.tape is not None:
             keep = [a_hi, a_lo] if c.tc_wgrad else [None, None]
 
@@ -347,7 +394,10 @@ class Engine:
                 if residual is not None:
                     residual.add_grad(dy, owned=False)
                 dy_scale = None
-                if c.bias is not None:
+                if c.bias is not None and out.grad_sum is not None:
+                    # dY came whole out of one BatchNorm-backward apply pass, which already summed it per channel
+                    ctx.pgrads[c.bias], dy_scale = out.grad_sum
+                elif c.bias is not None:
                     # bias gradient; the same pass over dY yields the power-of-two scale of the 3xFP16 data gradient
                     ctx.pgrads[c.bias], dy_scale = ops.channel_sum(dy, want_amax=True)
                 dy_hi = dy_lo = None
@@ -423,17 +473,19 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ hourglass topology
-    def bottleneck(self, ctx, x, prefix):
-        """Pre-activation residual block, reference hourglass.py:32-52."""
+    def bottleneck(self, ctx, x, prefix, out_bn=None):
+        """Pre-activation residual block, reference hourglass.py:32-52. out_bn: the block output goes straight into a
+        BatchNorm (the next block's bn1): conv3's epilogue then carries its statistics too."""
         has_ds = (prefix + ".downsample.0") in self.convs
         skip = self.conv(ctx, x, prefix + ".downsample.0") if has_ds else x
-        y = self.conv(ctx, x, prefix + ".conv1", prefix + ".bn1", relu=True)
-        y = self.conv(ctx, y, prefix + ".conv2", prefix + ".bn2", relu=True)
-        return self.conv(ctx, y, prefix + ".conv3", prefix + ".bn3", relu=True, residual=skip)
+        y = self.conv(ctx, x, prefix + ".conv1", prefix + ".bn1", relu=True, out_bn=prefix + ".bn2")
+        y = self.conv(ctx, y, prefix + ".conv2", prefix + ".bn2", relu=True, out_bn=prefix + ".bn3")
+        return self.conv(ctx, y, prefix + ".conv3", prefix + ".bn3", relu=True, residual=skip, out_bn=out_bn)
 
-    def residual_seq(self, ctx, x, prefix, nblocks):
+    def residual_seq(self, ctx, x, prefix, nblocks, out_bn=None):
         for i in range(nblocks):
-            x = self.bottleneck(ctx, x, "%s.%d" % (prefix, i))
+            nxt = "%s.%d.bn1" % (prefix, i + 1) if i + 1 < nblocks else out_bn
+            x = self.bottleneck(ctx, x, "%s.%d" % (prefix, i), out_bn=nxt)
         return x
 
     def hourglass(self, ctx, n, x, prefix, nblocks):
@@ -454,11 +506,13 @@ class Engine:
         else:
             up1 = self.residual_seq(ctx, x, "%s.%d.0" % (prefix, n - 1), nblocks)
         low1 = self.maxpool(ctx, x)
-        low1 = self.residual_seq(ctx, low1, "%s.%d.1" % (prefix, n - 1), nblocks)
+        # low1 feeds a BatchNorm directly (the next level's skip branch / the innermost block): statistics from the epilogue
+        low1 = self.residual_seq(ctx, low1, "%s.%d.1" % (prefix, n - 1), nblocks, out_bn=True)
         if n > 1:
             low2 = self.hourglass(ctx, n - 1, low1, prefix, nblocks)
         else:
-            low2 = self.residual_seq(ctx, low1, "%s.%d.3" % (prefix, n - 1), nblocks)
+            low2 = self.residual_seq(ctx, low1, "%s.%d.3" % (prefix, n - 1), nblocks,
+                                     out_bn="%s.%d.2.0.bn1" % (prefix, n - 1))
         low3 = self.residual_seq(ctx, low2, "%s.%d.2" % (prefix, n - 1), nblocks)
         if done is not None:
             torch.cuda.current_stream().wait_event(done)
@@ -487,19 +541,19 @@ class Engine:
         x = self.bn_act(ctx, x, "bn1", relu=True)
         x = self.residual_seq(ctx, x, "layer1", 1)
         x = self.maxpool(ctx, x)
-        x = self.residual_seq(ctx, x, "layer2", 1)
-        x = self.residual_seq(ctx, x, "layer3", 1)
+        x = self.residual_seq(ctx, x, "layer2", 1, out_bn="layer3.0.bn1")
+        x = self.residual_seq(ctx, x, "layer3", 1, out_bn=True)
         outs = []
         for i in range(net.num_stacks):
             y = self.hourglass(ctx, 4, x, "hg.%d.hg" % i, nb)
             y = self.residual_seq(ctx, y, "res.%d" % i, nb)
-            y = self.conv(ctx, y, "fc.%d.0" % i)
+            y = self.conv(ctx, y, "fc.%d.0" % i, out_bn="fc.%d.1" % i)
             y = self.bn_act(ctx, y, "fc.%d.1" % i, relu=True)
             score = self.conv(ctx, y, "score.%d" % i)
             outs.append(score)
             if i < net.num_stacks - 1:
                 t = self.conv(ctx, y, "fc_.%d" % i, residual=x)
-                x = self.conv(ctx, score, "score_.%d" % i, residual=t)
+                x = self.conv(ctx, score, "score_.%d" % i, residual=t, out_bn=True)
         return outs
 
     def prepare_stem(self, img_nchw, shared_stem):
@@ -528,6 +582,7 @@ class Engine:
         ctx = _Ctx()
         ctx.shared_stem = shared_stem
         ctx.training = training
+        ctx.sync = self._sync_spec() if training else None
         ctx.passes = precision_passes()
         ctx.tape = [] if record_tape else None
         if training:
@@ -545,6 +600,18 @@ class Engine:
             torch._foreach_add_(ctx.nbt, 1)
         ctx.outs = outs
         return ctx
+
+    def _sync_spec(self):
+        """(process group or None for the default, world size) when SyncBN is on and there is more than one rank."""
+        import torch.distributed as dist
+        g = self.bn_sync_group
+        if g is None and not BN_SYNC:
+            return None
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        group = None if (g is None or g is True) else g
+        world = dist.get_world_size(group)
+        return (group, world) if world > 1 else None
 
     def backward(self, ctx, out_grads_nhwc, wgrad_stream=None):
         """out_grads_nhwc: list (per stack) of NHWC gradient tensors or None. Returns {param: grad}.
@@ -566,6 +633,7 @@ class Engine:
 class _Ctx:
     def __init__(self):
         self.training = False
+        self.sync = None
         self.passes = 3
         self.tape = None
         self.weights = None

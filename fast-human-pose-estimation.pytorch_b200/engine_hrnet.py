@@ -46,19 +46,20 @@ class HRNetEngine(Engine):
     # ------------------------------------------------------------------ blocks
     def _skip(self, ctx, x, prefix):
         if (prefix + ".downsample.0") in self.convs:
-            y = self.conv(ctx, x, prefix + ".downsample.0")
+            y = self.conv(ctx, x, prefix + ".downsample.0", out_bn=prefix + ".downsample.1")
             return self.bn_act(ctx, y, prefix + ".downsample.1", relu=False)
         return x
 
+    # every HRNet convolution feeds a BatchNorm (post-activation blocks): out_bn lets the conv epilogue carry its statistics
     def basic_block(self, ctx, x, p):
-        y = self.conv(ctx, x, p + ".conv1")
-        y = self.conv(ctx, y, p + ".conv2", p + ".bn1", relu=True)
+        y = self.conv(ctx, x, p + ".conv1", out_bn=p + ".bn1")
+        y = self.conv(ctx, y, p + ".conv2", p + ".bn1", relu=True, out_bn=p + ".bn2")
         return self.bn_add_act(ctx, y, p + ".bn2", self._skip(ctx, x, p))
 
     def bottleneck_post(self, ctx, x, p):
-        y = self.conv(ctx, x, p + ".conv1")
-        y = self.conv(ctx, y, p + ".conv2", p + ".bn1", relu=True)
-        y = self.conv(ctx, y, p + ".conv3", p + ".bn2", relu=True)
+        y = self.conv(ctx, x, p + ".conv1", out_bn=p + ".bn1")
+        y = self.conv(ctx, y, p + ".conv2", p + ".bn1", relu=True, out_bn=p + ".bn2")
+        y = self.conv(ctx, y, p + ".conv3", p + ".bn2", relu=True, out_bn=p + ".bn3")
         return self.bn_add_act(ctx, y, p + ".bn3", self._skip(ctx, x, p))
 
     def block_seq(self, ctx, x, prefix):
@@ -76,7 +77,7 @@ class HRNetEngine(Engine):
         while ("%s.%d.0" % (prefix, n)) in self.convs:
             n += 1
         for k in range(n):
-            x = self.conv(ctx, x, "%s.%d.0" % (prefix, k))
+            x = self.conv(ctx, x, "%s.%d.0" % (prefix, k), out_bn="%s.%d.1" % (prefix, k))
             x = self.bn_act(ctx, x, "%s.%d.1" % (prefix, k), relu=(relu_last or k < n - 1))
         return x
 
@@ -94,7 +95,7 @@ class HRNetEngine(Engine):
                 if j == i:
                     terms.append((xs[j], 0))
                 elif j > i:
-                    t = self.conv(ctx, xs[j], fp + ".0")
+                    t = self.conv(ctx, xs[j], fp + ".0", out_bn=fp + ".1")
                     t = self.bn_act(ctx, t, fp + ".1", relu=False)
                     terms.append((t, j - i))
                 else:
@@ -114,7 +115,7 @@ class HRNetEngine(Engine):
             # like the reference forward (pose_hrnet.py:432-452) every non-None transition reads the LAST previous
             # branch; None keeps branch i
             if (tp + ".0") in self.convs:          # same resolution, width change: Sequential(conv, BN, ReLU)
-                t = self.conv(ctx, prev[-1], tp + ".0")
+                t = self.conv(ctx, prev[-1], tp + ".0", out_bn=tp + ".1")
                 xs.append(self.bn_act(ctx, t, tp + ".1", relu=True))
             elif (tp + ".0.0") in self.convs:      # new lower-resolution branch: chain of stride-2 conv+BN+ReLU
                 xs.append(self.conv_bn_chain(ctx, prev[-1], tp, relu_last=True))
@@ -131,7 +132,7 @@ class HRNetEngine(Engine):
             x = Var(ops.nchw_to_nhwc(img_nchw))
         x = self.conv(ctx, x, "conv1", need_dx=False)
         x = self.bn_act(ctx, x, "bn1", relu=True)
-        x = self.conv(ctx, x, "conv2")
+        x = self.conv(ctx, x, "conv2", out_bn="bn2")
         x = self.bn_act(ctx, x, "bn2", relu=True)
         x = self.block_seq(ctx, x, "layer1")
         ys = [x]

@@ -199,14 +199,44 @@ def weight_prep_f16_both(w_oihw):
     return (f_hi, f_lo), (d_hi, d_lo)
 
 
+CONV_STATS = os.environ.get("FPD_CONV_STATS", "1") != "0"   # BatchNorm statistics of conv outputs from the conv epilogue
+
+
+def conv2d_tc_h_stats_blocks(B, H, W, Cin, Cout, k, f16):
+    """Number of per-CTA partial blocks conv2d_tc_h(..., stats_part=) writes; 0 if the shape cannot carry statistics."""
+    if not CONV_STATS:
+        return 0
+    return int(N.lib().fpd_conv2d_tc_h_stats_blocks(B, H, W, Cin, Cout, k, int(f16)))
+
+
+def bn_finalize_sums(part, nblocks, pivot, P, gamma, beta, eps, running_mean=None, running_var=None, momentum=0.1):
+    """BatchNorm finalize from the per-CTA column sums of a producing conv's epilogue (conv2d_tc_h(stats_part=...)).
+    Returns (mean, var_biased, scale, shift, invstd); updates the running statistics like nn.BatchNorm2d."""
+    C = part.shape[1]
+    dev = part.device
+    mean = torch.empty(C, dtype=torch.float32, device=dev)
+    var, scale, shift, invstd = (torch.empty_like(mean) for _ in range(4))
+    N.check(N.lib().fpd_bn_finalize_sums(_p(part), int(nblocks), _p(pivot), int(P), C, _p(gamma), _p(beta), float(eps),
+                                         float(momentum), _p(running_mean), _p(running_var), _p(mean), _p(var), _p(scale),
+                                         _p(shift), _p(invstd), _stream()), "bn_finalize_sums")
+    return mean, var, scale, shift, invstd
+
+
 def conv2d_tc_h(x, w_hi, w_lo, ksize, mean=None, scale=None, shift=None, relu=False, bias=None, residual=None,
-                relu_mask=None, out=None, out_scale=1.0, in_scale=None):
+                relu_mask=None, out=None, out_scale=1.0, in_scale=None, stats_part=None, stats_pivot=None):
     """y = conv(relu?((x-mean)*scale+shift)) on the generation-5 kernel (csrc/conv_tc5.cu). The operand precision
     follows the weight dtype: float16 hi/lo -> 3xFP16 (kind::f16), float32 containers -> 3xTF32."""
     B, H, W, Cin = x.shape
     Cout = w_hi.shape[1]
     f16 = w_hi.dtype == torch.float16
     y = out if out is not None else torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
+    if stats_part is not None:
+        # forward convolution + per-channel sums of its output (the next BatchNorm's batch statistics) from the epilogue
+        assert relu_mask is None and in_scale is None and stats_part.dtype == torch.float64
+        N.check(N.lib().fpd_conv2d_tc_h_stats(_p(x), _p(mean), _p(scale), _p(shift), int(relu), _p(w_hi), _p(w_lo),
+                                              int(f16), _p(bias), _p(residual), _p(y), float(out_scale), B, H, W, Cin,
+                                              Cout, ksize, _p(stats_part), _p(stats_pivot), _stream()), "conv2d_tc_h_stats")
+        return y
     N.check(N.lib().fpd_conv2d_tc_h(_p(x), _p(mean), _p(scale), _p(shift), int(relu), _p(w_hi), _p(w_lo), int(f16),
                                     _p(bias), _p(residual), _p(relu_mask), _p(y), float(out_scale), _p(in_scale), B, H,
                                     W, Cin, Cout, ksize, _stream()), "conv2d_tc_h")
@@ -342,15 +372,35 @@ def bn_bwd_reduce(da, x, mean, invstd, scale, shift, relu):
     return sums
 
 
-def bn_bwd(da, x, mean, invstd, scale, shift, gamma, relu, accumulate_into=None):
-    """Returns (dx, dgamma, dbeta) for y = relu?(bn(x)) given da = dL/dy (train-mode batch statistics)."""
+BN_APPLY_SUM = os.environ.get("FPD_BN_APPLY_SUM", "1") != "0"   # bias-gradient sums + dY scale out of the BN-backward apply pass
+
+
+def bn_bwd(da, x, mean, invstd, scale, shift, gamma, relu, accumulate_into=None, sync_mean=None, want_dx_sum=False):
+    """Returns (dx, dgamma, dbeta) for y = relu?(bn(x)) given da = dL/dy (train-mode batch statistics).
+    sync_mean: optional callable sums[2C] -> the MEAN over ranks of the per-rank sums (SyncBN, parallel.allreduce_avg):
+    the batch-statistics terms of dx then use the statistics of the global batch (global sum / global count =
+    rank-mean of the sums / local count), while dgamma / dbeta stay this rank's sums (the gradient all-reduce averages
+    them like every other parameter gradient)."""
     C = x.shape[-1]
     P = x.numel() // C
     sums = bn_bwd_reduce(da, x, mean, invstd, scale, shift, relu)
+    apply_sums = sums if sync_mean is None else sync_mean(sums)
     dx = accumulate_into if accumulate_into is not None else torch.empty_like(x)
+    if want_dx_sum and accumulate_into is None and FUSED_REDUCE and BN_APPLY_SUM and C % 4 == 0:
+        # the same pass also yields sum_pixels(dx) per channel and the operand scale of dx: what channel_sum(dx,
+        # want_amax=True) would compute for the bias gradient / 3xFP16 data gradient of the conv that produced x
+        dx_sum = torch.empty(C, dtype=torch.float32, device=x.device)
+        amax = torch.empty(2, dtype=torch.float32, device=x.device)
+        ws = _ws.get(N.lib().fpd_channel_reduce_workspace_bytes(P, C), x.device)
+        N.check(N.lib().fpd_bn_bwd_apply_sum(_p(da), _p(x), _p(mean), _p(invstd), _p(scale), _p(shift), _p(gamma), int(relu),
+                                             _p(apply_sums), _p(dx), _p(dx_sum), _p(amax), P, C, _p(ws), ws.numel(),
+                                             _stream()), "bn_bwd_apply_sum")
+        return dx, sums[C:], sums[:C], (dx_sum, amax)
     N.check(N.lib().fpd_bn_bwd_apply(_p(da), _p(x), _p(mean), _p(invstd), _p(scale), _p(shift), _p(gamma), int(relu),
-                                     _p(sums), int(accumulate_into is not None), _p(dx), P, C, _stream()),
+                                     _p(apply_sums), int(accumulate_into is not None), _p(dx), P, C, _stream()),
             "bn_bwd_apply")
+    if want_dx_sum:
+        return dx, sums[C:], sums[:C], None
     return dx, sums[C:], sums[:C]
 
 

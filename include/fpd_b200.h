@@ -111,6 +111,21 @@ int fpd_conv2d_tc_h_set_profile_buffer(long long* device_buf);
 int fpd_weight_prep_f16(const float* w_oihw, void* w_hi, void* w_lo, int O, int I, int k, int for_dgrad,
                         fpd_stream_t stream);
 
+/* Forward convolution that also produces the BatchNorm batch statistics of its OUTPUT (train mode): the per-channel sums
+ * come out of the epilogue (per-CTA partial blocks, merged by fpd_bn_finalize_sums), so the separate statistics pass
+ * over the tensor that nn.BatchNorm2d (lib/models/hourglass.py:18-26) implies disappears. Arguments as fpd_conv2d_tc_h
+ * (no relu_mask / in_scale: forward only); stat_part: device double[fpd_conv2d_tc_h_stats_blocks(...)][Cout][2];
+ * stat_pivot: device float[Cout] or NULL, any per-channel value near the expected mean (improves conditioning only). */
+int fpd_conv2d_tc_h_stats_blocks(int B, int H, int W, int Cin, int Cout, int ksize, int f16);   /* 0 = shape not supported */
+int fpd_conv2d_tc_h_stats(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
+                          int pre_relu, const void* w_hi, const void* w_lo, int f16, const float* bias,
+                          const float* residual, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
+                          int ksize, double* stat_part, const float* stat_pivot, fpd_stream_t stream);
+/* mean = pivot + S1/P, var = S2/P - (S1/P)^2 from those partial sums, then the BatchNorm finalize (scale = gamma * invstd,
+ * shift = beta, running statistics update with `momentum`); outputs as fpd_bn_stats_fused. */
+int fpd_bn_finalize_sums(const double* part, int nblocks, const float* pivot, int64_t P, int C, const float* gamma,
+                         const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                         float* mean, float* var_biased, float* scale, float* shift, float* invstd, fpd_stream_t stream);
 /* Leaner forms of fpd_channel_sum / fpd_bn_bwd_reduce / (fpd_bn_stats + fpd_bn_finalize): the BatchNorm statistics'
  * second stage and the module's finalize (affine + running statistics) run as one kernel (division-free fp64 merge), and
  * the channel sum can also return the operand scale of the 3xFP16 gradient convolutions: amax_scale (nullable float[2])
@@ -207,6 +222,13 @@ int fpd_channel_sum(const float* dy, int64_t P, int C, float scale, float* out, 
 int fpd_bn_bwd_reduce(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
                       const float* shift, int relu, int64_t P, int C, float* sums, void* workspace,
                       size_t workspace_bytes, fpd_stream_t stream);
+/* fpd_bn_bwd_apply (fresh dx, no accumulation) that also reduces its output in the same pass: dx_sum[C] = per-channel sum
+ * of dx -- the bias gradient of the convolution whose output this BatchNorm consumed (hourglass.py:20-27) -- and
+ * amax_scale[2] = {S, 1/S}, the power-of-two operand scale of that convolution's 3xFP16 data gradient (as
+ * fpd_channel_sum_fused; nullable). workspace: fpd_channel_reduce_workspace_bytes(P, C). */
+int fpd_bn_bwd_apply_sum(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
+                         const float* shift, const float* gamma, int relu, const float* sums, float* dx, float* dx_sum,
+                         float* amax_scale, int64_t P, int C, void* workspace, size_t workspace_bytes, fpd_stream_t stream);
 int fpd_bn_bwd_apply(const float* da, const float* x, const float* mean, const float* invstd, const float* scale,
                      const float* shift, const float* gamma, int relu, const float* sums, int accumulate, float* dx,
                      int64_t P, int C, fpd_stream_t stream);

@@ -79,3 +79,80 @@ def test_two_rank_step_matches_single_process_emulation():
     for rank, same, ok_emul, err in res:
         assert same, "replicas diverged"
         assert ok_emul, "DDP update differs from the single-process emulation: %.3e" % err
+
+
+def _sync_worker(rank, world, port, q, use_graph):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import fpd_b200  # noqa: F401
+    from fpd_b200 import ops, parallel
+    from fpd_b200.lib.models import hourglass as H
+    from fpd_b200.train_step import FPDTrainStep
+    from bench import synthetic_batch
+    torch.manual_seed(9)
+    student = H.get_pose_net(_cfg(64, 2), True).cuda()
+    teacher = H.get_pose_net(_cfg(64, 1), False).cuda()
+    parallel.broadcast_module(student, 0)
+    parallel.broadcast_module(teacher, 0)
+    init = {k: v.clone() for k, v in student.state_dict().items()}
+    per = 2
+    x, t, w = (v.cuda() for v in synthetic_batch(per * world, 300, 128, 128))       # the GLOBAL batch, same on every rank
+    lo, hi = parallel.shard_range(per * world, rank, world)
+    student.engine().bn_sync_group = True                                             # SyncBN over the default group
+    step = FPDTrainStep(student, teacher, alpha=0.5, lr=1e-3, use_graph=use_graph)
+    losses = step.step(x[lo:hi].contiguous(), t[lo:hi].contiguous(), w[lo:hi].contiguous()).clone()
+    torch.cuda.synchronize()
+    outs = [o.clone() for o in step.last_outs]
+    flat = step.flat.flat.clone()
+    lsum = losses.clone()
+    dist.all_reduce(lsum)
+    res = {"rank": rank}
+    if rank == 0:
+        # one process, the concatenated batch, ordinary (local) BatchNorm
+        ref = H.get_pose_net(_cfg(64, 2), True).cuda()
+        ref.load_state_dict(init)
+        rstep = FPDTrainStep(ref, teacher, alpha=0.5, lr=1e-3, use_graph=False)
+        rstep.world = 1
+        rl = rstep._body(x, t, w.reshape(per * world, -1)).clone()
+        r_outs = [o.clone() for o in rstep.last_outs]
+        ops.adam_flat(rstep.flat.flat, rstep.flat.grad, rstep.exp_avg, rstep.exp_avg_sq, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1)
+        torch.cuda.synchronize()
+        rel = lambda a, b: ((a - b).abs().max() / b.abs().max()).item()                # noqa: E731
+        res["out"] = max(rel(o, r[lo:hi]) for o, r in zip(outs, r_outs))
+        res["loss"] = rel(lsum / world, rl)
+        res["w"] = rel(flat, rstep.flat.flat)
+        sd, rsd = student.state_dict(), ref.state_dict()
+        res["rv"] = rel(sd["hg.1.hg.0.3.0.bn2.running_var"], rsd["hg.1.hg.0.3.0.bn2.running_var"])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    res["same"] = all(torch.equal(gathered[0], g) for g in gathered)
+    q.put(res)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_syncbn_two_ranks_equal_one_rank_on_the_concatenated_batch(use_graph):
+    """FPD_BN_SYNC / Engine.bn_sync_group: with the BatchNorm statistics (forward) and the BatchNorm-backward sums
+    exchanged, a 2-rank step on two half batches is the 1-rank step on the whole batch (<= 1e-5: only the reduction order
+    differs) -- heat-maps, loss, running statistics and the weights after Adam."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 1000 + (50 if use_graph else 0)
+    procs = [ctx.Process(target=_sync_worker, args=(r, world, port, q, use_graph)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for r in res:
+        assert r["same"], "replicas diverged"
+        if r["rank"] == 0:
+            assert r["out"] < 1e-5 and r["loss"] < 1e-5 and r["rv"] < 1e-5, r
+            assert r["w"] < 1e-4, r      # Adam's g / (|g| + eps) amplifies last-bit gradient differences of tiny entries

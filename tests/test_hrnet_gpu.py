@@ -153,3 +153,40 @@ def test_hrnet_fpd_train_step_matches_oracle_losses():
     assert abs(total - ref_total.item()) < TOL * abs(ref_total.item())
     assert not torch.equal(w0, step.flat.flat)
     assert torch.isfinite(step.flat.flat).all()
+
+
+def test_hrnet_w32_w48_fpd_train_step_at_baseline_widths():
+    """BASELINE configs[3] at the real widths (w32 student, frozen w48 teacher, 256x192) and a small batch: the whole
+    train step runs (incl. the wide stride-2 convolutions' weight gradients, Cout 256 / 384) and its loss terms match
+    the oracle."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from fpd_b200.train_step import FPDTrainStep
+    from oracle import hourglass_oracle as O
+    from oracle import hrnet_oracle as HO
+    torch.manual_seed(23)
+    student, teacher = _net("w32"), _net("w48")
+    for m in teacher.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+    B = 2
+    x = torch.randn(B, 3, 256, 192, device="cuda")
+    target = torch.rand(B, 17, 64, 48, device="cuda")
+    tw = (torch.rand(B, 17, 1, device="cuda") > 0.2).float()
+    s_sd = HO.annotate_strides({k: v.clone() for k, v in student.state_dict().items()})
+    t_sd = HO.annotate_strides({k: v.clone() for k, v in teacher.state_dict().items()})
+    with torch.no_grad():
+        out = HO.hrnet(s_sd, x, training=True)
+        tout = HO.hrnet(t_sd, x, training=False)
+        ref_total, ref_pose, ref_kd = O.fpd_loss([out], target, tw, tout, 0.5)
+    step = FPDTrainStep(student, teacher, alpha=0.5, lr=1e-3, use_graph=True)
+    w0 = step.flat.flat.clone()
+    losses = step.step(x, target, tw)
+    torch.cuda.synchronize()
+    pose, kd, total = [float(v) for v in losses.cpu()]
+    assert abs(pose - ref_pose.item()) < TOL * abs(ref_pose.item())
+    assert abs(kd - ref_kd.item()) < TOL * abs(ref_kd.item())
+    assert abs(total - ref_total.item()) < TOL * abs(ref_total.item())
+    assert torch.isfinite(step.flat.flat).all() and not torch.equal(w0, step.flat.flat)
+    assert torch.isfinite(step.flat.grad).all() and float(step.flat.grad.abs().max()) > 0

@@ -324,6 +324,14 @@ def test_bn_train_forward_backward(shape):
     scale, shift, invstd = o.bn_finalize(mean, var, gamma.detach(), beta.detach(), 1e-5, B * H * W, rm2, rv2, 0.1)
     a_hi, a_lo = o.affine_act_split(xh, scale, shift, relu=True, mean=mean)
     dx, dgamma, dbeta = o.bn_bwd(nhwc(dy), xh, mean, invstd, scale, shift, gamma.detach(), True)
+    # the apply pass that also reduces its own output: identical dx, its per-channel sum, and the same power-of-two operand
+    # scale channel_sum(dx, want_amax=True) derives
+    dx2, dgamma2, dbeta2, dsum = o.bn_bwd(nhwc(dy), xh, mean, invstd, scale, shift, gamma.detach(), True, want_dx_sum=True)
+    assert dsum is not None and torch.equal(dx2, dx) and torch.equal(dgamma2, dgamma) and torch.equal(dbeta2, dbeta)
+    ref_sum, ref_scale = o.channel_sum(dx, want_amax=True)
+    # sum of dx over the batch is ~0 by construction (BatchNorm removes the mean): compare on the scale of sum |dx|
+    assert ((dsum[0].double() - dx.double().sum((0, 1, 2))).abs().max() / dx.double().abs().sum((0, 1, 2)).max()).item() < 1e-6
+    assert torch.equal(dsum[1], ref_scale)
     torch.cuda.synchronize()
     xd = x.detach().double()
     assert relerr(mean, xd.mean((0, 2, 3)).float()) < 1e-6
@@ -598,3 +606,56 @@ def test_stem_im2col_tensor_core_path(cfg):
     torch.cuda.synchronize()
     assert relerr(nchw(y), y_ref) < 2e-5
     assert relerr(dw, dw_ref) < 2e-5
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 64, 64, 64, 3), (2, 16, 16, 128, 64, 1), (3, 8, 8, 64, 128, 1), (5, 4, 4, 64, 64, 3),
+                                   (32, 64, 64, 128, 128, 1), (2, 64, 48, 32, 32, 3), (2, 64, 64, 16, 128, 1)])
+@pytest.mark.parametrize("f16", [True, False])
+@pytest.mark.parametrize("with_pivot", [False, True])
+def test_conv2d_tc_h_epilogue_batchnorm_statistics(shape, f16, with_pivot):
+    """conv_tc_h_kernel<.., kStats>: the output is bit-identical to the plain kernel's, and the per-channel statistics
+    finalized from the epilogue's partial sums equal nn.BatchNorm2d's batch statistics of that output (mean, biased
+    variance, scale / shift, running-statistics update) -- including ragged batch tails (B % images-per-tile != 0) and a
+    large common-mode offset with a pivot."""
+    B, H, W, Cin, Cout, k = shape
+    o = ops()
+    nblk = o.conv2d_tc_h_stats_blocks(B, H, W, Cin, Cout, k, f16)
+    if nblk == 0:
+        pytest.skip("shape does not carry epilogue statistics")
+    g = torch.Generator(device="cuda").manual_seed(77)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * (1.0 / (Cin * k * k) ** 0.5)
+    bias = torch.randn(Cout, device="cuda", generator=g) * (30.0 if with_pivot else 1.0)     # common-mode offset
+    res = torch.randn(B, H, W, Cout, device="cuda", generator=g)
+    mean_in = torch.randn(Cin, device="cuda", generator=g) * 0.1
+    scale_in = torch.rand(Cin, device="cuda", generator=g) + 0.5
+    shift_in = torch.randn(Cin, device="cuda", generator=g) * 0.1
+    prep = o.weight_prep_f16 if f16 else o.weight_prep
+    w_hi, w_lo = prep(w)
+    kw = dict(mean=mean_in, scale=scale_in, shift=shift_in, relu=True, bias=bias, residual=res)
+    y_plain = o.conv2d_tc_h(x, w_hi, w_lo, k, **kw)
+    part = torch.full((nblk, Cout, 2), float("nan"), dtype=torch.float64, device="cuda")
+    pivot = (bias + 0.3).contiguous() if with_pivot else None
+    y = o.conv2d_tc_h(x, w_hi, w_lo, k, stats_part=part, stats_pivot=pivot, **kw)
+    assert torch.equal(y, y_plain)
+    gamma = torch.rand(Cout, device="cuda", generator=g) + 0.5
+    beta = torch.randn(Cout, device="cuda", generator=g)
+    rm = torch.randn(Cout, device="cuda", generator=g)
+    rv = torch.rand(Cout, device="cuda", generator=g) + 0.5
+    rm0, rv0 = rm.clone(), rv.clone()
+    mean, var, scale, shift, invstd = o.bn_finalize_sums(part, nblk, pivot, B * H * W, gamma, beta, 1e-5, rm, rv, 0.1)
+    torch.cuda.synchronize()
+    yd = y.double().reshape(-1, Cout)
+    ref_mean, ref_var = yd.mean(0), yd.var(0, unbiased=False)
+    assert ((mean.double() - ref_mean).abs() / (ref_var.sqrt() + 1e-30)).max() < 2e-6      # relative to the channel's std
+    tol_var = 2e-6 * (1.0 + float((((ref_mean - (pivot.double() if with_pivot else 0.0)) ** 2) / ref_var).max()))
+    assert relerr(var, ref_var) < max(tol_var, 1e-5), (relerr(var, ref_var), tol_var)
+    ref_invstd = 1.0 / torch.sqrt(ref_var + 1e-5)
+    assert relerr(invstd, ref_invstd) < 1e-5 and relerr(scale, gamma.double() * ref_invstd) < 1e-5
+    assert torch.equal(shift, beta)
+    n = B * H * W
+    assert relerr(rm, 0.9 * rm0.double() + 0.1 * ref_mean) < 1e-5
+    assert relerr(rv, 0.9 * rv0.double() + 0.1 * ref_var * n / (n - 1)) < 1e-5
+    # and equal to the separate statistics pass it replaces
+    m2, v2, s2, _, i2 = o.bn_stats_finalize(y, gamma, beta, 1e-5)
+    assert relerr(mean, m2) < 1e-5 and relerr(var, v2) < 2e-5

@@ -115,7 +115,7 @@ def test_bench_configuration_step_matches_oracle():
     d_64 = torch.cat([(p64[k].detach() - w64_before[k]).reshape(-1) for k in names]).cpu()
     e_got = (d_got - d_64).norm() / d_64.norm()
     e_32 = (d_32 - d_64).norm() / d_64.norm()
-    assert e_got <= P.K_L2 * e_32 + 1e-4, (e_got.item(), e_32.item())
+    assert e_got <= 1.5 * e_32 + 1e-4, (e_got.item(), e_32.item())
     assert abs(l64[0] - total) < TOL * abs(l64[0])
     print("bench-config parity: grads l2 ours %.3e fp32 %.3e, worst tensor ratio %.2f, adam update ours %.3e fp32 %.3e" % (
         rep["l2_ours"], rep["l2_fp32"], rep["worst_ratio"], e_got.item(), e_32.item()))
