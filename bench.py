@@ -191,13 +191,19 @@ def measured_peaks():
 # CPU legs: the reference's own modules (oracle/_ref) on the host cores -- cpu_baseline and --impl reference.
 # The ONLY place bench.py touches oracle/.
 # --------------------------------------------------------------------------------------------------
-def cpu_threads():
-    """Thread count of the CPU legs: FPD_CPU_THREADS, else the best point of the committed sweep
-    (profiles/r2_cpu_thread_sweep.txt: tools/cpu_thread_sweep.py on the B200 box's host), else all cores up to 32."""
+# Fastest (batch per step, threads) of the reference's CPU path on the B200 box's host (128 schedulable CPUs, Xeon 8562Y+),
+# from the committed sweep profiles/r2_cpu_thread_sweep.txt (tools/cpu_thread_sweep.py): more threads or larger batches
+# are SLOWER per image there (hg_fpd: 6.7 img/s at B=4 / 16 threads, 3.0 at B=8, 1.6 at B=32; 1.1 with 64 threads), so the
+# CPU legs run the sample size and thread count the reference is fastest with. FPD_CPU_THREADS / --batch override.
+CPU_BEST = {"hg_fpd": (4, 16), "hg_mse_s1": (2, 8), "hrnet_fpd": (8, 16), "hg_infer": (8, 16)}
+
+
+def cpu_threads(name=None):
     n = int(os.environ.get("FPD_CPU_THREADS", "0"))
     if n:
         return n
-    return min(32, len(os.sched_getaffinity(0)))
+    best = CPU_BEST.get(name, (0, 16))[1]
+    return min(best, len(os.sched_getaffinity(0)))
 
 
 class CpuReference:
@@ -208,7 +214,7 @@ class CpuReference:
         from oracle import ref_modules as R
         c = CONFIGS[name]
         self.c, self.B, self.kind = c, batch, ("reference" if R.available() else "port")
-        self.threads = cpu_threads()
+        self.threads = cpu_threads(name)
         torch.set_num_threads(self.threads)
         torch.manual_seed(seed)
         self.as_written = as_written
@@ -332,15 +338,17 @@ def run_reference(args, rank):
         return
     name = args.config
     c = CONFIGS[name]
-    B = args.batch or c["batch"]
+    # one step = one bounded sample of the workload: the batch size the CPU path is FASTEST with on this host (CPU_BEST)
+    B = args.batch or CPU_BEST[name][0]
     ips, n, threads, kind = time_cpu(name, B, args.steps, args.warmup, max_seconds=float(os.environ.get("FPD_CPU_MAX_S", "900")))
     sample = ("%s: the reference's own lib/models + lib/core/loss modules (oracle/_ref), loop body of lib/core/function.py, "
-              "teacher under no_grad, batch %d per step, %d timed steps after %d warm-up, fp32, %d threads" % (
+              "teacher under no_grad, %d images per step (the sample size and thread count the CPU path is fastest with, "
+              "profiles/r2_cpu_thread_sweep.txt), %d timed steps after %d warm-up, fp32, %d threads" % (
                   kind, B, n, args.warmup, threads))
     line = {"impl": "reference", "metric": "images/sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
             "steps": n, "warmup": args.warmup, "ms_per_step": 1000.0 * B / ips, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(name, args.gpus, B),
+            "config": workload_config(name, args.gpus, c["batch"]),
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if c["kind"] == "train" and c["teacher"] is not None and os.environ.get("FPD_CPU_AS_WRITTEN", "0") != "0":
@@ -558,8 +566,8 @@ def run_b200(args, rank, local_rank, world):
         line["roofline"] = {"error": repr(exc), "step_frac_of_f16_peak": step_frac}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            cb = min(B, int(os.environ.get("FPD_CPU_BASELINE_B", "8")))
-            ips, n, threads, kind = time_cpu(name, cb, steps=3, warmup=1, max_seconds=25.0)
+            cb = min(B, CPU_BEST[name][0])
+            ips, n, threads, kind = time_cpu(name, cb, steps=4, warmup=1, max_seconds=25.0)
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": kind,
                                     "sample": "the reference's own modules on the host cores: %d timed steps of batch %d of the "
                                               "same workload (teacher under no_grad), fp32, %d threads; `--impl reference` "

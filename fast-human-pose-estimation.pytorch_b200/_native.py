@@ -76,6 +76,8 @@ _SIGNATURES = {
     "fpd_maxpool2x2_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "fpd_upsample2x_add": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     "fpd_upsample2x_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "fpd_subsample2": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "fpd_upsample_zero2": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "fpd_nchw_to_nhwc": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "fpd_nchw_to_nhwc_flipw": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "fpd_nhwc_to_nchw": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),

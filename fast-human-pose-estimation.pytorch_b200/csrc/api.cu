@@ -308,6 +308,12 @@ int fpd_upsample2x_add(const float* up1, const float* low, float* out, int B, in
 int fpd_upsample2x_bwd(const float* dout, float* dlow, int B, int H, int W, int C, fpd_stream_t stream) {
   return upsample2x_bwd(dout, dlow, B, H, W, C, S(stream));
 }
+int fpd_subsample2(const float* x, float* y, int B, int H, int W, int C, fpd_stream_t stream) {
+  return subsample2(x, y, B, H, W, C, S(stream));
+}
+int fpd_upsample_zero2(const float* dy, float* dx, int B, int Ho, int Wo, int C, fpd_stream_t stream) {
+  return upsample_zero2(dy, dx, B, Ho, Wo, C, S(stream));
+}
 int fpd_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, fpd_stream_t stream) {
   return nchw_to_nhwc(x, y, B, C, H, W, S(stream));
 }

@@ -699,6 +699,34 @@ __global__ void upsample2x_bwd_kernel(const float4* __restrict__ dout, float4* _
   }
 }
 
+// Stride-2 convolutions on the stride-1 tensor-core kernels: y_s2[ho, wo] = y_s1[2 ho, 2 wo] (k = 3, pad = 1), so the
+// forward is the stride-1 convolution followed by this even-position pick, and the backward feeds the stride-1 data /
+// weight gradient kernels with dY scattered back to the even positions of a zero tensor.
+__global__ void subsample2_kernel(const float4* __restrict__ x, float4* __restrict__ y, int B, int Ho, int Wo, int L) {
+  const int64_t n = (int64_t)B * Ho * Wo * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % L);
+    int64_t t = i / L;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int64_t b = t / Ho;
+    y[i] = __ldg(x + ((b * (2 * Ho) + 2 * ho) * (2 * Wo) + 2 * wo) * L + cx);
+  }
+}
+__global__ void upsample_zero2_kernel(const float4* __restrict__ dy, float4* __restrict__ dx, int B, int Ho, int Wo, int L) {
+  const int64_t n = (int64_t)B * (2 * Ho) * (2 * Wo) * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % L);
+    int64_t t = i / L;
+    const int w = (int)(t % (2 * Wo)); t /= (2 * Wo);
+    const int h = (int)(t % (2 * Ho));
+    const int64_t b = t / (2 * Ho);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (((w | h) & 1) == 0) v = __ldg(dy + ((b * Ho + (h >> 1)) * Wo + (w >> 1)) * L + cx);
+    dx[i] = v;
+  }
+}
+
 // NCHW <-> NHWC through a 32x33 shared-memory transpose tile (coalesced on both sides)
 __global__ void transpose_cs_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols, int flip_w) {
   // in: [batch][rows][cols] -> out: [batch][cols][rows]; flip_w > 0 (NCHW -> NHWC only): cols = H * flip_w pixels and the
@@ -858,8 +886,13 @@ __global__ void upsample_bwd_kernel(const float4* __restrict__ dout, float4* __r
 //      pose_hrnet.py:281): cols[b,ho,wo, (kh*k+kw)*Cin + ci] = x[b, ho*s+kh-p, wo*s+kw-p, ci], zero outside the image and
 //      for the K padding. The result is an ordinary NHWC tensor with Kpad channels, so the stem becomes a 1x1
 //      convolution on the tensor-core path (forward and weight gradient).
-__global__ void im2col_kernel(const float* __restrict__ x, float4* __restrict__ cols, int B, int H, int W, int Cin,
-                              int k, int stride, int pad, int Ho, int Wo, int Kpad) {
+// KK / CIN > 0: compile-time kernel size and channel count (the two stems that exist: 7x7x3 and 3x3x3) -- the four
+// divisions / modulos per element become multiply-shifts (the generic form spent most of its 350 us on them).
+template <int KK, int CIN>
+__global__ void im2col_kernel(const float* __restrict__ x, float4* __restrict__ cols, int B, int H, int W, int Cin_rt,
+                              int k_rt, int stride, int pad, int Ho, int Wo, int Kpad) {
+  const int Cin = CIN > 0 ? CIN : Cin_rt;
+  const int k = KK > 0 ? KK : k_rt;
   const int K = k * k * Cin;
   const int kq = Kpad / 4;
   const int64_t n = (int64_t)B * Ho * Wo * kq;
@@ -987,6 +1020,22 @@ int upsample2x_bwd(const float* dout, float* dlow, int B, int H, int W, int C, c
   const int64_t n = (int64_t)B * (H / 2) * (W / 2) * (C / 4);
   upsample2x_bwd_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const float4*)dout, (float4*)dlow, B, H / 2, W / 2,
                                                               C / 4);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int subsample2(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "subsample2: need C %% 4 == 0 and even H, W (C=%d H=%d W=%d)", C, H, W);
+  const int64_t n = (int64_t)B * (H / 2) * (W / 2) * (C / 4);
+  subsample2_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const float4*)x, (float4*)y, B, H / 2, W / 2, C / 4);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int upsample_zero2(const float* dy, float* dx, int B, int Ho, int Wo, int C, cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0, "upsample_zero2: C=%d must be a multiple of 4", C);
+  const int64_t n = (int64_t)B * (2 * Ho) * (2 * Wo) * (C / 4);
+  upsample_zero2_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const float4*)dy, (float4*)dx, B, Ho, Wo, C / 4);
   FPD_LAUNCH_CHECK();
   return FPD_OK;
 }
@@ -1264,7 +1313,12 @@ int im2col(const float* x, float* cols, int B, int H, int W, int Cin, int k, int
   FPD_REQUIRE(Kpad % 4 == 0 && Kpad >= k * k * Cin, "im2col: Kpad=%d must be a multiple of 4 and >= k*k*Cin", Kpad);
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const int64_t n = (int64_t)B * Ho * Wo * (Kpad / 4);
-  im2col_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, (float4*)cols, B, H, W, Cin, k, stride, pad, Ho, Wo, Kpad);
+  if (k == 7 && Cin == 3)
+    im2col_kernel<7, 3><<<grid_for(n, 256), 256, 0, stream>>>(x, (float4*)cols, B, H, W, Cin, k, stride, pad, Ho, Wo, Kpad);
+  else if (k == 3 && Cin == 3)
+    im2col_kernel<3, 3><<<grid_for(n, 256), 256, 0, stream>>>(x, (float4*)cols, B, H, W, Cin, k, stride, pad, Ho, Wo, Kpad);
+  else
+    im2col_kernel<0, 0><<<grid_for(n, 256), 256, 0, stream>>>(x, (float4*)cols, B, H, W, Cin, k, stride, pad, Ho, Wo, Kpad);
   FPD_LAUNCH_CHECK();
   return FPD_OK;
 }

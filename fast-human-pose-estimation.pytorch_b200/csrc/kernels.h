@@ -112,6 +112,8 @@ int maxpool2x2_bwd(const float* x, const float* dy, float* dx, int accumulate, i
 int upsample2x_add(const float* up1, const float* low, float* out, int B, int H, int W, int C,
                    cudaStream_t stream);  // H,W = output size
 int upsample2x_bwd(const float* dout, float* dlow, int B, int H, int W, int C, cudaStream_t stream);
+int subsample2(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream);        // y[ho,wo] = x[2ho,2wo]
+int upsample_zero2(const float* dy, float* dx, int B, int Ho, int Wo, int C, cudaStream_t stream);  // adjoint of subsample2
 int nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream);
 int nchw_to_nhwc_flipw(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream);   // + W mirror
 int nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream);

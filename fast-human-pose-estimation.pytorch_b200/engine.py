@@ -70,8 +70,14 @@ class Var:
         self.add_grad(dx, True)
 
 
+# stride-2 3x3 convolutions (HRNet stem / transitions / fuse down paths) on the stride-1 tensor-core kernels:
+# y = subsample2(conv_s1(x)); 4x the necessary MACs, but on tcgen05 instead of the CUDA-core fallback (which was 97 % of
+# the HRNet step: profiles/r2b_timeline_hrnet.txt)
+STRIDE2_TC = os.environ.get("FPD_STRIDE2_TC", "1") != "0"
+
+
 class ConvRef:
-    __slots__ = ("name", "weight", "bias", "k", "stride", "pad", "cin", "cout")
+    __slots__ = ("name", "weight", "bias", "k", "stride", "pad", "cin", "cout", "as_s1")
 
     def __init__(self, name, mod):
         self.name = name
@@ -82,6 +88,13 @@ class ConvRef:
         self.pad = mod.padding[0]
         self.cin = mod.in_channels
         self.cout = mod.out_channels
+        # run as a stride-1 convolution + even-position pick (decided per call: needs even H, W)
+        self.as_s1 = (STRIDE2_TC and self.stride == 2 and self.k == 3 and self.pad == 1 and self.cin >= 4
+                      and mod.kernel_size[1] == 3 and mod.stride[1] == 2)
+
+    @property
+    def s1(self):
+        return self.stride == 1 or self.as_s1
 
     @property
     def im2col_kpad(self):
@@ -93,18 +106,17 @@ class ConvRef:
 
     @property
     def tc_fwd(self):
-        return self.stride == 1 and self.pad == self.k // 2 and ops.conv2d_tc_supported(self.cin, self.cout, self.k,
-                                                                                         fused=FUSED_FWD)
+        return self.s1 and self.pad == self.k // 2 and ops.conv2d_tc_supported(self.cin, self.cout, self.k,
+                                                                                fused=FUSED_FWD)
 
     @property
     def tc_dgrad(self):
-        return self.stride == 1 and self.pad == self.k // 2 and ops.conv2d_tc_supported(self.cout, self.cin, self.k,
-                                                                                         fused=FUSED_DGRAD)
+        return self.s1 and self.pad == self.k // 2 and ops.conv2d_tc_supported(self.cout, self.cin, self.k,
+                                                                                fused=FUSED_DGRAD)
 
     @property
     def tc_wgrad(self):
-        return self.stride == 1 and self.pad == self.k // 2 and ops.conv2d_wgrad_tc_supported(self.cin, self.cout,
-                                                                                               self.k)
+        return self.s1 and self.pad == self.k // 2 and ops.conv2d_wgrad_tc_supported(self.cin, self.cout, self.k)
 
 
 class BNRef:
@@ -317,6 +329,19 @@ class Engine:
         out_bn: name of a train-mode BatchNorm that will consume y (True: some BatchNorm, name unknown) -- the conv then
         also emits y's per-channel sums from its epilogue (Var.stat_sums), pivoted on that module's running mean."""
         c = self.convs[conv_name]
+        if c.as_s1 and not getattr(ctx, "_in_s1", False):
+            H_, W_ = x.data.shape[1], x.data.shape[2]
+            if (H_ % 2 == 0 and W_ % 2 == 0 and c.cout % 4 == 0 and c.tc_fwd and residual is None
+                    and not (bn_name is None and c.im2col_kpad)):
+                # stride 2 = stride-1 convolution on the tensor cores + even-position pick (recorded as two tape entries:
+                # the pick's backward scatters dY into a zero tensor, the stride-1 conv's backward is the ordinary one)
+                ctx._in_s1 = True
+                try:
+                    full = self.conv(ctx, x, conv_name, bn_name, relu, residual, need_dx, out_bn=None)
+                finally:
+                    ctx._in_s1 = False
+                return self.subsample2(ctx, full)
+        s1_ok = c.stride == 1 or getattr(ctx, "_in_s1", False)
         split = ctx.passes == 3
         scale = shift = mean = None
         aff = None
@@ -355,7 +380,7 @@ class Engine:
                                                          pad=c.pad), owned=True)
                 ctx.tape.append(bwd_stem)
             return out
-        if c.tc_fwd:
+        if c.tc_fwd and s1_ok:
             w_hi, w_lo, use_h = ctx.weights.fwd(c, x.data.shape[1], x.data.shape[2],
                                                 also_dgrad=ctx.tape is not None and need_dx)
             stat_sums = None
@@ -382,10 +407,14 @@ class Engine:
             a = ops.affine_act(x.data, scale, shift, relu, mean=mean) if bn_name is not None else x.data
             y = ops.conv2d_simt_fwd(a, c.weight.detach(), bias=bias, residual=res, stride=c.stride, pad=c.pad)
         out = Var(y)
-        if c.tc_fwd:
+        if c.tc_fwd and s1_ok:
             out.stat_sums = stat_sums
+        tc_wgrad = c.tc_wgrad and s1_ok
+        tc_dgrad = c.tc_dgrad and s1_ok
+        in_s1 = c.as_s1 and s1_ok            # stride-2 conv running as stride 1 + pick: dY arrives zero-upsampled
+        stride_eff = 1 if in_s1 else c.stride
         if ctx.tape is not None:
-            keep = [a_hi, a_lo] if c.tc_wgrad else [None, None]
+            keep = [a_hi, a_lo] if tc_wgrad else [None, None]
 
             def bwd():
                 dy = out.grad
@@ -401,10 +430,10 @@ class Engine:
                     # bias gradient; the same pass over dY yields the power-of-two scale of the 3xFP16 data gradient
                     ctx.pgrads[c.bias], dy_scale = ops.channel_sum(dy, want_amax=True)
                 dy_hi = dy_lo = None
-                if (c.tc_wgrad and not FUSED_WGRAD) or (need_dx and c.tc_dgrad and not FUSED_DGRAD):
+                if (tc_wgrad and not FUSED_WGRAD) or (need_dx and tc_dgrad and not FUSED_DGRAD):
                     dy_hi, dy_lo = ops.affine_act_split(dy, split=split)
                 # ---- weight gradient
-                if c.tc_wgrad and FUSED_WGRAD and ctx.wgrad_stream is not None:
+                if tc_wgrad and FUSED_WGRAD and ctx.wgrad_stream is not None:
                     # dW (and the bias gradient) are leaves of the backward graph: compute them on a side stream so they
                     # fill the SMs that the small-grid kernels of the critical dgrad/BN chain leave idle
                     main = torch.cuda.current_stream()
@@ -415,10 +444,10 @@ class Engine:
                         ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc_fused(x.data, dy, c.k, mean=mean, scale=scale,
                                                                          shift=shift, relu=relu, passes=ctx.passes)
                     ctx.keepalive.append(dy)     # dy must outlive the side-stream kernel (released after the join)
-                elif c.tc_wgrad and FUSED_WGRAD:
+                elif tc_wgrad and FUSED_WGRAD:
                     ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc_fused(x.data, dy, c.k, mean=mean, scale=scale, shift=shift,
                                                                      relu=relu, passes=ctx.passes)
-                elif c.tc_wgrad:
+                elif tc_wgrad:
                     if keep[0] is None:  # fused forward did not materialise the operand pair: make it now
                         keep[0], keep[1] = ops.affine_act_split(x.data, scale, shift, relu, split=split, mean=mean)
                     ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc(keep[0], keep[1], dy_hi, dy_lo, c.k)
@@ -426,11 +455,14 @@ class Engine:
                 else:
                     a_full = (ops.affine_act(x.data, scale, shift, relu, mean=mean) if bn_name is not None
                               else x.data)
-                    ctx.pgrads[c.weight] = ops.conv2d_simt_wgrad(a_full, dy, c.k, stride=c.stride, pad=c.pad)
+                    # CUDA-core fallback; for a stride-2 conv in stride-1 mode go back to the compact dY (the even
+                    # positions of the zero-upsampled one) and the true stride: a quarter of the work
+                    dy_w = ops.subsample2(dy) if in_s1 else dy
+                    ctx.pgrads[c.weight] = ops.conv2d_simt_wgrad(a_full, dy_w, c.k, stride=c.stride, pad=c.pad)
                 if not need_dx:
                     return
                 # ---- data gradient w.r.t. the conv input a = act(bn(x))
-                if c.tc_dgrad:
+                if tc_dgrad:
                     wd_hi, wd_lo, use_h = ctx.weights.dgrad(c, dy.shape[1], dy.shape[2], f16_ok=dy_scale is not None)
                     if FUSED_DGRAD:
                         if use_h:
@@ -441,11 +473,22 @@ class Engine:
                     else:
                         da = ops.conv2d_tc(dy_hi, dy_lo, wd_hi, wd_lo, c.k)
                 else:
-                    da = ops.conv2d_simt_dgrad(dy, c.weight.detach(), x.data.shape[1:3], stride=c.stride, pad=c.pad)
+                    da = ops.conv2d_simt_dgrad(dy, c.weight.detach(), x.data.shape[1:3], stride=stride_eff, pad=c.pad)
                 if bn_name is not None:
                     self._bn_backward(ctx, x, bn_name, relu, da, aff)
                 else:
                     x.add_grad(da, owned=True)
+            ctx.tape.append(bwd)
+        return out
+
+    def subsample2(self, ctx, x):
+        """Even-position pick that turns a stride-1 3x3 convolution into the stride-2 one (see ConvRef.as_s1)."""
+        out = Var(ops.subsample2(x.data))
+        if ctx.tape is not None:
+            def bwd():
+                if out.grad is None:
+                    return
+                x.add_grad(ops.upsample_zero2(out.grad), owned=True)
             ctx.tape.append(bwd)
         return out
 
@@ -633,6 +676,7 @@ class Engine:
 class _Ctx:
     def __init__(self):
         self.training = False
+        self._in_s1 = False
         self.sync = None
         self.passes = 3
         self.tape = None

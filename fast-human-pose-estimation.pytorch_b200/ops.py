@@ -199,12 +199,17 @@ def weight_prep_f16_both(w_oihw):
     return (f_hi, f_lo), (d_hi, d_lo)
 
 
-CONV_STATS = os.environ.get("FPD_CONV_STATS", "1") != "0"   # BatchNorm statistics of conv outputs from the conv epilogue
+# BatchNorm statistics of conv outputs from the conv epilogue: "0" off, "1" every tensor-core conv, "3x3" only the 3x3
+# convolutions (tensor-bound: their epilogue has slack; the 1x1 convolutions are epilogue-bound). Measured on the bench
+# configuration (profiles/r2b_fusion_ab.txt): all on 34.4 ms/step, statistics off 34.0, both fusions off 33.9 -- the step
+# is bound by the total time of the full-grid kernels, so removing the small statistics pass does not pay for the extra
+# epilogue work; correct and tested, off by default.
+CONV_STATS = os.environ.get("FPD_CONV_STATS", "0").lower()
 
 
 def conv2d_tc_h_stats_blocks(B, H, W, Cin, Cout, k, f16):
     """Number of per-CTA partial blocks conv2d_tc_h(..., stats_part=) writes; 0 if the shape cannot carry statistics."""
-    if not CONV_STATS:
+    if CONV_STATS == "0" or (CONV_STATS == "3x3" and k != 3):
         return 0
     return int(N.lib().fpd_conv2d_tc_h_stats_blocks(B, H, W, Cin, Cout, k, int(f16)))
 
@@ -372,7 +377,10 @@ def bn_bwd_reduce(da, x, mean, invstd, scale, shift, relu):
     return sums
 
 
-BN_APPLY_SUM = os.environ.get("FPD_BN_APPLY_SUM", "1") != "0"   # bias-gradient sums + dY scale out of the BN-backward apply pass
+# bias-gradient sums + dY operand scale out of the BN-backward apply pass (one launch and one read of dx less per conv);
+# measured neutral (34.35 vs 34.42 ms/step: the reduction-geometry kernel keeps fewer loads in flight than the plain
+# elementwise apply), so off by default
+BN_APPLY_SUM = os.environ.get("FPD_BN_APPLY_SUM", "0") != "0"
 
 
 def bn_bwd(da, x, mean, invstd, scale, shift, gamma, relu, accumulate_into=None, sync_mean=None, want_dx_sum=False):
@@ -440,6 +448,22 @@ def upsample2x_bwd(dout, out=None):
     d = out if out is not None else torch.empty((B, H // 2, W // 2, C), dtype=torch.float32, device=dout.device)
     N.check(N.lib().fpd_upsample2x_bwd(_p(dout), _p(d), B, H, W, C, _stream()), "upsample2x_bwd")
     return d
+
+
+def subsample2(x, out=None):
+    """y[b, ho, wo] = x[b, 2 ho, 2 wo]: the stride-2 pick after a stride-1 3x3 convolution (pad 1)."""
+    B, H, W, C = x.shape
+    y = out if out is not None else torch.empty((B, H // 2, W // 2, C), dtype=torch.float32, device=x.device)
+    N.check(N.lib().fpd_subsample2(_p(x), _p(y), B, H, W, C, _stream()), "subsample2")
+    return y
+
+
+def upsample_zero2(dy, out=None):
+    """Adjoint of subsample2: dy scattered to the even positions of a zero [B, 2Ho, 2Wo, C] tensor."""
+    B, Ho, Wo, C = dy.shape
+    dx = out if out is not None else torch.empty((B, 2 * Ho, 2 * Wo, C), dtype=torch.float32, device=dy.device)
+    N.check(N.lib().fpd_upsample_zero2(_p(dy), _p(dx), B, Ho, Wo, C, _stream()), "upsample_zero2")
+    return dx
 
 
 def nchw_to_nhwc(x, out=None):

@@ -240,6 +240,12 @@ int fpd_maxpool2x2_bwd(const float* x, const float* dy, float* dx, int accumulat
 int fpd_upsample2x_add(const float* up1, const float* low, float* out, int B, int H, int W, int C,
                        fpd_stream_t stream); /* H,W = output size */
 int fpd_upsample2x_bwd(const float* dout, float* dlow, int B, int H, int W, int C, fpd_stream_t stream);
+/* Stride-2 3x3 convolutions (HRNet stem / transition / fuse down paths, lib/models/pose_hrnet.py:213-239,281-284,355-370)
+ * on the stride-1 tensor-core kernels: y = subsample2(conv_s1(x)) picks the even positions (x: [B,H,W,C] -> y:
+ * [B,H/2,W/2,C]); upsample_zero2 is its adjoint (dY scattered to the even positions of a zero [B,2Ho,2Wo,C] tensor), which
+ * then feeds the stride-1 data- and weight-gradient kernels. */
+int fpd_subsample2(const float* x, float* y, int B, int H, int W, int C, fpd_stream_t stream);
+int fpd_upsample_zero2(const float* dy, float* dx, int B, int Ho, int Wo, int C, fpd_stream_t stream);
 int fpd_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, fpd_stream_t stream);
 /* Same, with the image mirrored along W on the way (the flipped input of the flip test, lib/core/function.py:218-221:
  * np.flip(input, 3)), so the second forward needs no separate flip pass. */

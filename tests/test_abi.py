@@ -105,7 +105,7 @@ def test_bench_reference_arm_contract_on_cpu(capsys):
             assert line["impl"] == "reference" and line["metric"] == "images/sec" and line["unit"] == "images/s"
             assert line["value"] > 0 and line["higher_is_better"] is True and line["n_gpus"] == 1
             assert line["steps"] == 1 and line["warmup"] == 0
-            assert line["config"] == bench.workload_config(name, 1, B)          # the GPU arm's config keys
+            assert line["config"] == bench.workload_config(name, 1, bench.CONFIGS[name]["batch"])   # = the GPU arm's config
             assert line["cpu_baseline"]["kind"] == ("reference" if R.available() else "port")
             assert line["cpu_baseline"]["cores"] >= 1
             assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0

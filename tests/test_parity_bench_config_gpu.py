@@ -302,3 +302,48 @@ def test_teacher_reload_after_capture_is_seen_by_the_graph():
     sdict = step.state_dict()
     step.load_state_dict(sdict)
     assert step.step_count == 4
+
+
+def test_optional_fusions_give_the_same_step():
+    """FPD_CONV_STATS (BatchNorm statistics from the conv epilogue) and FPD_BN_APPLY_SUM (bias-gradient sums out of the
+    BatchNorm-backward apply pass) are off by default (measured neutral on the bench step); switched on they must
+    reproduce the default path: same losses, heat-maps, running statistics and gradients up to reduction order."""
+    import fpd_b200  # noqa: F401
+    from bench import synthetic_batch
+    from fpd_b200 import ops
+    from fpd_b200.lib.models import hourglass as H
+    from fpd_b200.train_step import FPDTrainStep
+    torch.manual_seed(12)
+    init_s = {k: v.clone() for k, v in H.get_pose_net(_cfg(128, 2), True).state_dict().items()}
+    init_t = {k: v.clone() for k, v in H.get_pose_net(_cfg(64, 1), False).state_dict().items()}
+    x, t, w = (v.cuda() for v in synthetic_batch(4, 9, 256, 256))
+
+    def run(stats, apply_sum):
+        old = ops.CONV_STATS, ops.BN_APPLY_SUM
+        ops.CONV_STATS, ops.BN_APPLY_SUM = stats, apply_sum
+        try:
+            s = H.get_pose_net(_cfg(128, 2), True)
+            s.load_state_dict(init_s)
+            tt = H.get_pose_net(_cfg(64, 1), False)
+            tt.load_state_dict(init_t)
+            st = FPDTrainStep(s.cuda(), tt.cuda(), lr=1e-3, use_graph=False)
+            n0 = ops.N.lib().fpd_launch_count()
+            losses = st.step(x, t, w).clone()
+            torch.cuda.synchronize()
+            return (losses.cpu(), [o.clone() for o in st.last_outs], st.flat.grad.clone(),
+                    {k: v.clone() for k, v in s.state_dict().items()}, int(ops.N.lib().fpd_launch_count() - n0))
+        finally:
+            ops.CONV_STATS, ops.BN_APPLY_SUM = old
+    base = run("0", False)
+    for stats, apply_sum in (("1", False), ("3x3", False), ("0", True), ("1", True)):
+        got = run(stats, apply_sum)
+        assert got[4] < base[4], "the fused variants launch fewer kernels (%d vs %d)" % (got[4], base[4])
+        assert torch.allclose(got[0], base[0], rtol=2e-5, atol=0), (stats, apply_sum, got[0], base[0])
+        for a, b in zip(got[1], base[1]):
+            assert P.rel_max(a, b) < 1e-4, (stats, apply_sum)
+        # gradients: the statistics differ in the last bits, which re-decides a few ReLU masks (tests/_parity.py): whole-
+        # gradient relative L2, not a per-element bound
+        l2 = ((got[2].double() - base[2].double()).norm() / base[2].double().norm()).item()
+        assert l2 < 3e-2, (stats, apply_sum, l2)
+        assert P.rel_max(got[3]["hg.1.hg.0.3.0.bn2.running_var"], base[3]["hg.1.hg.0.3.0.bn2.running_var"]) < 1e-5
+        assert P.rel_max(got[3]["layer3.0.bn1.running_mean"], base[3]["layer3.0.bn1.running_mean"]) < 1e-5

@@ -17,13 +17,22 @@ print(json.dumps({"config": %r, "batch": %d, "threads": threads, "images_per_s":
 '''
 
 
+THREADS = (4, 8, 16, 24, 32, 64)
+
+
 def main():
     ncpu = len(os.sched_getaffinity(0))
     print("# host: %d schedulable CPUs; %s" % (ncpu, open("/proc/cpuinfo").read().split("model name")[1].split("\n")[0].strip(": \t")))
-    plan = [("hg_fpd", 8, 2, 40.0), ("hg_fpd", 32, 1, 60.0), ("hg_mse_s1", 2, 10, 15.0), ("hg_infer", 16, 2, 30.0),
-            ("hrnet_fpd", 8, 2, 40.0)]
+    global THREADS
+    if len(sys.argv) > 1 and sys.argv[1] == "small":      # second pass: small batches around the best thread counts
+        THREADS = (8, 16, 24)
+        plan = [("hg_fpd", 2, 3, 30.0), ("hg_fpd", 4, 3, 30.0), ("hrnet_fpd", 2, 3, 30.0), ("hrnet_fpd", 4, 3, 30.0),
+                ("hg_infer", 4, 3, 20.0), ("hg_infer", 8, 3, 20.0)]
+    else:
+        plan = [("hg_fpd", 8, 2, 40.0), ("hg_fpd", 32, 1, 60.0), ("hg_mse_s1", 2, 10, 15.0), ("hg_infer", 16, 2, 30.0),
+                ("hrnet_fpd", 8, 2, 40.0)]
     for name, B, steps, mx in plan:
-        for t in (4, 8, 16, 24, 32, 64):
+        for t in THREADS:
             if t > ncpu:
                 continue
             if B == 32 and t not in (8, 16, 32):

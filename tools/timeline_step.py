@@ -40,16 +40,18 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--tag", default="r2")
     ap.add_argument("--eager", action="store_true")
+    ap.add_argument("--config", default="hg_fpd")
     args = ap.parse_args()
     import fpd_b200  # noqa: F401
-    from fpd_b200.lib.models import hourglass as H
     from fpd_b200.train_step import FPDTrainStep
-    from bench import cfg, synthetic_batch
-    torch.manual_seed(0)
-    student = H.get_pose_net(cfg(128, 4), True).cuda()
-    teacher = H.get_pose_net(cfg(256, 8), False).cuda()
-    step = FPDTrainStep(student, teacher, use_graph=not args.eager)
-    x, t, w = (v.cuda() for v in synthetic_batch(args.batch, 0))
+    import bench
+    from bench import synthetic_batch
+    c = bench.CONFIGS[args.config]
+    student, teacher = bench.build_models(args.config, torch.device("cuda"))
+    step = FPDTrainStep(student, teacher, lr=c["lr"], use_graph=not args.eager)
+    if args.batch <= 0:
+        args.batch = c["batch"]
+    x, t, w = (v.cuda() for v in synthetic_batch(args.batch, 0, c["H"], c["W"], c["J"]))
     for _ in range(4):
         step.step(x, t, w)
     torch.cuda.synchronize()
@@ -111,6 +113,7 @@ def main():
         f[2] += d * min(g, 148)
         f[3] += 1 if g < 148 else 0
     lines = []
+    lines.append("config %s" % args.config)
     lines.append("one %s FPD step, B=%d: %d kernels, span %.3f ms, summed kernel time %.3f ms" % (
         "eager" if args.eager else "graph-replayed", args.batch, len(ev), span / 1e3, sum(e[1] for e in ev) / 1e3))
     lines.append("SM cover (time-integral of min(148, sum of running grids)) = %.3f of 148 x span" % (cover / (148 * span)))
