@@ -58,6 +58,15 @@ CONFIGS = {
         family="hourglass", student=(128, 4), teacher=None, batch=128, H=256, W=256, J=16, lr=0.0,
         flop_per_image=15.629e9, kind="infer",
         roof=dict(cin=64, cout=64, k=3, h=64, w=64)),
+    # --- diagnostics (not BASELINE configs): the two halves of hg_fpd on their own
+    "diag_student": dict(
+        workload="[diagnostic] hourglass s4 f128 train, MSE only, 256x256, batch 32 (the student half of hg_fpd)",
+        family="hourglass", student=(128, 4), teacher=None, batch=32, H=256, W=256, J=16, lr=2.5e-4,
+        flop_per_image=23.44e9, kind="train", roof=dict(cin=64, cout=64, k=3, h=64, w=64)),
+    "diag_teacher": dict(
+        workload="[diagnostic] hourglass s8 f256 forward only (no flip), 256x256, batch 32 (the teacher half of hg_fpd)",
+        family="hourglass", student=(256, 8), teacher=None, batch=32, H=256, W=256, J=16, lr=0.0,
+        flop_per_image=56.189e9, kind="infer", flip=False, roof=dict(cin=128, cout=128, k=3, h=64, w=64)),
 }
 CONV_H_3X3_DRAM_BYTES = 87.09e6   # dram__bytes_read + write, conv_tc_h 3x3 128->128 @64x64 B=32: profiles/r1c_prof_conv_h_3x3.md
 
@@ -472,8 +481,8 @@ def run_b200(args, rank, local_rank, world):
     else:
         from fpd_b200.infer_step import FlipTestInference
         boxes = torch.from_numpy(synthetic_boxes(1024, 1)).to(dev)
-        inf = FlipTestInference(student, MPII_FLIP_PAIRS, shift_heatmap=True, flip_test=True, use_graph=graph_ok,
-                                want_avg=False)
+        inf = FlipTestInference(student, MPII_FLIP_PAIRS, shift_heatmap=True, flip_test=c.get("flip", True),
+                                use_graph=graph_ok, want_avg=False)
         run_dev = lambda: inf(xd, boxes, 0.6)                                # noqa: E731
         idx_host = torch.empty(B, c["J"], dtype=torch.int32).pin_memory()
         max_host = torch.empty(B, c["J"], dtype=torch.float32).pin_memory()

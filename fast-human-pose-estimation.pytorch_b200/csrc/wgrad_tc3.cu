@@ -15,6 +15,11 @@
 //     per pixel instead of five times and a stage carries 5 x 12 MMAs (~1900 cycles) per barrier round trip.
 // GEMM per tap: D[ci][co] += A_tap^T[ci][32 px] * dY[32 px][co], both operands MN-major (pixel rows of 128 bytes =
 // 32 channels), M = Cin (64 or 128), N = Cout, K = 8 pixels per MMA, 3xTF32 (hi/lo pairs, operands split in place).
+// Cin = 32 ("pair" mode): UMMA has no M = 32, so TWO taps share one M = 64 instruction -- the descriptor's leading-
+// dimension byte offset, normally the distance to the next 32-channel block, is set to the distance between the two
+// taps' start rows in the SAME halo block (128 B for a +1 step along w), which the address-keyed swizzle allows just as
+// it allows arbitrary start rows. Pairs (0,1) (2,3) (4,5) (6,7) (7,8): all nine taps accumulate in one CTA
+// (5 x Cout TMEM columns); rows 0..31 of the last pair repeat tap 7 and are dropped.
 //
 // Warp roles (448 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2-5 epilogue (after the K loop),
 // warps 6-13 operand transform. Split-K over pixel blocks across CTAs; wgrad_reduce3_kernel sums the partials in a fixed
@@ -45,6 +50,7 @@ struct Wgrad3Params {
   int splits, kt_per_split;
   int tmem_cols;
   int lane_map;             // accumulator row -> TMEM lane mapping for M = 64 (see acc_lane)
+  int pair;                 // Cin = 32: two taps share one M = 64 MMA (see the MMA issuer); 0 otherwise
   float* partial;           // [splits][9][Cin][Cout]
   const float* pre_mean;
   const float* pre_scale;
@@ -102,8 +108,8 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int g = blockIdx.x % p.groups;          // tap group
   const int sp = blockIdx.x / p.groups;         // K split
-  const int tap0 = g * p.tg;
-  const int ntaps = min(p.tg, 9 - tap0);
+  const int tap0 = p.pair ? 0 : g * p.tg;
+  const int ntaps = p.pair ? 5 : min(p.tg, 9 - tap0);      // pair mode: five tap PAIRS
   const int kt0 = sp * p.kt_per_split;
   const int kt1 = min(kt0 + p.kt_per_split, p.num_ktiles);
   const int nkt = max(kt1 - kt0, 0);
@@ -153,7 +159,7 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc_tf32((uint32_t)p.Cin, (uint32_t)p.Cout, 1, 1);   // both operands MN-major
+    const uint32_t idesc = umma_idesc_tf32((uint32_t)(p.pair ? 64 : p.Cin), (uint32_t)p.Cout, 1, 1);   // both MN-major
     int s = 0;
     uint32_t ph = 0;
     for (int i = 0; i < nkt; ++i, s = (s + 1 == p.stages ? 0 : s + 1), ph ^= (s == 0)) {
@@ -165,19 +171,25 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const uint32_t x_lo = x_hi + (uint32_t)p.half_bytes;
         const uint32_t g_lo = g_hi + (uint32_t)p.half_bytes;
         for (int t = 0; t < ntaps; ++t) {
-          const int tap = tap0 + t;
+          const int tap = p.pair ? (t < 4 ? 2 * t : 7) : tap0 + t;      // pair mode: first tap of the pair
           const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+          // leading-dimension offset of the A operand: next 32-channel block, or (pair mode) the second tap's start row
+          uint32_t lbo = (uint32_t)p.xblk_bytes;
+          if (p.pair) {
+            const int tb = tap + 1, dh2 = tb / 3 - 1, dw2 = tb % 3 - 1;
+            lbo = (uint32_t)(((dh2 - dh) * p.halo_w + (dw2 - dw)) * 128);
+          }
           const uint32_t tmem_d = tmem_base + (uint32_t)(t * p.Cout);
 #pragma unroll
           for (int ks = 0; ks < kKp / 8; ++ks) {
             // the 8 pixels of this K step are consecutive along w: halo row of the first one, shifted by the tap
             const int prow = (ks * 8) / p.bw, pcol = (ks * 8) % p.bw;
             const uint32_t xoff = (uint32_t)(((prow + 1 + dh) * p.halo_w + pcol + 1 + dw) * 128);
-            const uint64_t da_hi = umma_desc_sw128_32b(x_hi + xoff, (uint32_t)p.xblk_bytes, 512);
+            const uint64_t da_hi = umma_desc_sw128_32b(x_hi + xoff, lbo, 512);
             const uint64_t db_hi = umma_desc_sw128_32b(g_hi + ks * 1024, kKp * 128, 512);
             uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
             if (split) {
-              const uint64_t da_lo = umma_desc_sw128_32b(x_lo + xoff, (uint32_t)p.xblk_bytes, 512);
+              const uint64_t da_lo = umma_desc_sw128_32b(x_lo + xoff, lbo, 512);
               const uint64_t db_lo = umma_desc_sw128_32b(g_lo + ks * 1024, kKp * 128, 512);
               umma_tf32_ss(tmem_d, da_lo, db_hi, idesc, acc);
               umma_tf32_ss(tmem_d, da_hi, db_lo, idesc, 1u);
@@ -195,14 +207,24 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   } else if (warp < 6) {
     // ===================== epilogue: accumulators -> fp32 partials [split][tap][ci][co] =====================
     const int q = warp & 3;
-    const int row = acc_row_of_lane(q * 32 + lane, p.Cin, p.lane_map);
+    const int M = p.pair ? 64 : p.Cin;
+    const int row = acc_row_of_lane(q * 32 + lane, M, p.lane_map);
     if (nkt > 0) {
       mbar_wait(done_bar, 0);
       tc_fence_after_sync();
     }
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int t = 0; t < ntaps; ++t) {
-      float* prow = p.partial + (((size_t)sp * 9 + tap0 + t) * p.Cin + (row < 0 ? 0 : row)) * p.Cout;
+      // pair mode: accumulator row = (which tap of the pair) * 32 + input channel; the last pair's first half repeats tap 7
+      int tap_of_row = tap0 + t, ci_of_row = row < 0 ? 0 : row;
+      bool keep = row >= 0 && row < M;
+      if (p.pair) {
+        const int half = ci_of_row >> 5;
+        tap_of_row = (t < 4 ? 2 * t : 7) + half;
+        ci_of_row &= 31;
+        if (t == 4 && half == 0) keep = false;
+      }
+      float* prow = p.partial + (((size_t)sp * 9 + tap_of_row) * p.Cin + ci_of_row) * p.Cout;
       for (int c0 = 0; c0 < p.Cout; c0 += 16) {
         uint32_t v[16];
         if (nkt > 0) {
@@ -212,7 +234,7 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = 0u;
         }
-        if (row >= 0 && row < p.Cin) {
+        if (keep) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
             *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
@@ -329,12 +351,15 @@ wgrad_reduce3_kernel(const float* __restrict__ partial, float* __restrict__ dw, 
 struct Plan3 {
   bool ok;
   int bw, bh, halo_w, halo_h, halo_px, cblks, nblk, xblk_bytes, half_bytes, stage_bytes, stages, groups, tg, tmem_cols;
+  int pair;
 };
 
 Plan3 plan3(int H, int W, int Cin, int Cout, int passes) {
   Plan3 pl{};
   pl.ok = false;
-  if (!(Cin == 64 || Cin == 128)) return pl;                   // M of the MMA
+  static const bool pair_ok = [] { const char* e = getenv("FPD_WGRAD3_PAIR"); return !(e && e[0] == '0'); }();
+  pl.pair = (Cin == 32 && pair_ok) ? 1 : 0;                    // two taps per M = 64 instruction
+  if (!(Cin == 64 || Cin == 128 || pl.pair)) return pl;        // M of the MMA
   if (Cout % 32 != 0 || Cout < 32 || Cout > 256) return pl;    // N of the MMA (multiple of 16), 32-channel TMA boxes
   if (W % 8 != 0) return pl;                                   // a K step = 8 pixels consecutive along w
   int bw = 8;
@@ -353,6 +378,10 @@ Plan3 plan3(int H, int W, int Cin, int Cout, int passes) {
   if (pl.stages < 2) return pl;
   pl.groups = (9 * Cout + 511) / 512;
   pl.tg = (9 + pl.groups - 1) / pl.groups;
+  if (pl.pair) {                  // five tap pairs, all in one CTA
+    pl.groups = 1;
+    pl.tg = 5;
+  }
   int tc = 32;
   while (tc < pl.tg * Cout) tc *= 2;
   if (tc > 512) return pl;
@@ -393,7 +422,7 @@ int wgrad_tc3_launch(const float* x, const float* pre_mean, const float* pre_sca
   p.halo_w = pl.halo_w; p.halo_h = pl.halo_h; p.halo_px = pl.halo_px;
   p.cblks = pl.cblks; p.nblk = pl.nblk; p.xblk_bytes = pl.xblk_bytes; p.half_bytes = pl.half_bytes;
   p.stage_bytes = pl.stage_bytes; p.stages = pl.stages;
-  p.groups = pl.groups; p.tg = pl.tg;
+  p.groups = pl.groups; p.tg = pl.tg; p.pair = pl.pair;
   p.splits = num_sms / pl.groups;
   if (p.splits < 1) p.splits = 1;
   if (p.splits > p.num_ktiles) p.splits = p.num_ktiles;

@@ -198,6 +198,9 @@ class Engine:
                 self.bns[name] = BNRef(name, m)
         self._eval_cache = None
         self._eval_cache_key = None
+        # True: the BatchNorm-backward apply pass always also reduces its output (sum + max |dx|): engines whose convolutions
+        # have no bias (HRNet) get the 3xFP16 operand scale of dY from it -- without it their data gradients run on 3xTF32
+        self.force_apply_sum = False
         self.bn_sync_group = None  # set to a process group (or True = default group) for SyncBN; FPD_BN_SYNC=1 does it globally
         self._generation = 0       # bumped by everything that writes parameters / buffers behind torch's back
         self._branch_streams = {}
@@ -297,7 +300,8 @@ class Engine:
                 from . import parallel
                 sync_mean = lambda sums: parallel.allreduce_avg(sums, ctx.sync[0])     # noqa: E731
             dx, dgamma, dbeta, dsum = ops.bn_bwd(da, x.data, mean, invstd, scale, shift, m.weight.detach(), relu,
-                                                 accumulate_into=tgt, sync_mean=sync_mean, want_dx_sum=True)
+                                                 accumulate_into=tgt, sync_mean=sync_mean,
+                                                 want_dx_sum="force" if self.force_apply_sum else True)
             ctx.pgrads[m.weight] = dgamma
             ctx.pgrads[m.bias] = dbeta
             x.set_or_merge(dx, tgt is not None)
@@ -413,6 +417,10 @@ class Engine:
         tc_dgrad = c.tc_dgrad and s1_ok
         in_s1 = c.as_s1 and s1_ok            # stride-2 conv running as stride 1 + pick: dY arrives zero-upsampled
         stride_eff = 1 if in_s1 else c.stride
+        wgrad_chunks = None                  # too wide for one tensor-core wgrad launch: one launch per channel chunk
+        if (ctx.tape is not None and not tc_wgrad and s1_ok and FUSED_WGRAD and c.pad == c.k // 2
+                and (bn_name is not None or not c.im2col_kpad)):
+            wgrad_chunks = ops.wgrad_channel_chunks(c.cin, c.cout, c.k)
         if ctx.tape is not None:
             keep = [a_hi, a_lo] if tc_wgrad else [None, None]
 
@@ -423,9 +431,12 @@ class Engine:
                 if residual is not None:
                     residual.add_grad(dy, owned=False)
                 dy_scale = None
-                if c.bias is not None and out.grad_sum is not None:
-                    # dY came whole out of one BatchNorm-backward apply pass, which already summed it per channel
-                    ctx.pgrads[c.bias], dy_scale = out.grad_sum
+                if out.grad_sum is not None:
+                    # dY came whole out of one BatchNorm-backward apply pass, which already summed it per channel and
+                    # derived its power-of-two operand scale
+                    dy_scale = out.grad_sum[1]
+                    if c.bias is not None:
+                        ctx.pgrads[c.bias] = out.grad_sum[0]
                 elif c.bias is not None:
                     # bias gradient; the same pass over dY yields the power-of-two scale of the 3xFP16 data gradient
                     ctx.pgrads[c.bias], dy_scale = ops.channel_sum(dy, want_amax=True)
@@ -447,6 +458,9 @@ class Engine:
                 elif tc_wgrad and FUSED_WGRAD:
                     ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc_fused(x.data, dy, c.k, mean=mean, scale=scale, shift=shift,
                                                                      relu=relu, passes=ctx.passes)
+                elif wgrad_chunks is not None:
+                    ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc_chunked(x.data, dy, c.k, wgrad_chunks, mean=mean, scale=scale,
+                                                                       shift=shift, relu=relu, passes=ctx.passes)
                 elif tc_wgrad:
                     if keep[0] is None:  # fused forward did not materialise the operand pair: make it now
                         keep[0], keep[1] = ops.affine_act_split(x.data, scale, shift, relu, split=split, mean=mean)
@@ -488,7 +502,11 @@ class Engine:
             def bwd():
                 if out.grad is None:
                     return
+                gs = out.grad_sum
+                fresh = x.grad is None
                 x.add_grad(ops.upsample_zero2(out.grad), owned=True)
+                if fresh and gs is not None:
+                    x.grad_sum = gs       # zeros add nothing: the per-channel sums and the maximum carry over unchanged
             ctx.tape.append(bwd)
         return out
 

@@ -12,6 +12,10 @@ from .engine import Engine, Var
 
 
 class HRNetEngine(Engine):
+    def __init__(self, net):
+        super().__init__(net)
+        self.force_apply_sum = True     # bias-free convolutions: dY's 3xFP16 operand scale comes from the BN-backward pass
+
     # ------------------------------------------------------------------ extra building blocks
     def bn_add_act(self, ctx, x, bn_name, residual, relu=True):
         aff = self._bn_affine(ctx, x, bn_name)

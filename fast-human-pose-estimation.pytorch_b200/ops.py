@@ -201,10 +201,9 @@ def weight_prep_f16_both(w_oihw):
 
 # BatchNorm statistics of conv outputs from the conv epilogue: "0" off, "1" every tensor-core conv, "3x3" only the 3x3
 # convolutions (tensor-bound: their epilogue has slack; the 1x1 convolutions are epilogue-bound). Measured on the bench
-# configuration (profiles/r2b_fusion_ab.txt): all on 34.4 ms/step, statistics off 34.0, both fusions off 33.9 -- the step
-# is bound by the total time of the full-grid kernels, so removing the small statistics pass does not pay for the extra
-# epilogue work; correct and tested, off by default.
-CONV_STATS = os.environ.get("FPD_CONV_STATS", "0").lower()
+# configuration (profiles/r2_fusion_ab.txt): every conv 34.4 ms/step, off 33.6-33.9, 3x3 only 33.1 -- the step is bound by
+# the total time of the full-grid kernels, so the statistics pay only where the epilogue is not the conv's own limit.
+CONV_STATS = os.environ.get("FPD_CONV_STATS", "3x3").lower()
 
 
 def conv2d_tc_h_stats_blocks(B, H, W, Cin, Cout, k, f16):
@@ -308,6 +307,37 @@ def conv2d_wgrad_tc_fused(x, dy, ksize, mean=None, scale=None, shift=None, relu=
     return dw
 
 
+def wgrad_channel_chunks(cin, cout, k):
+    """Split of the input channels into widths the tensor-core weight-gradient kernels take (M = Cin in {128, 64, 32}), for
+    convolutions that are too wide for one launch (HRNet: 256-channel 3x3). None if some remainder cannot be covered."""
+    if conv2d_wgrad_tc_supported(cin, cout, k):
+        return [cin]
+    chunks, rest = [], cin
+    for w in (128, 64, 32):
+        while rest >= w and conv2d_wgrad_tc_supported(w, cout, k):
+            chunks.append(w)
+            rest -= w
+    return chunks if rest == 0 and chunks else None
+
+
+def conv2d_wgrad_tc_chunked(x, dy, ksize, chunks, mean=None, scale=None, shift=None, relu=False, passes=3):
+    """dW of a wide convolution as one tensor-core weight-gradient launch per input-channel chunk: the chunk of x is made
+    contiguous (a strided copy -- these tensors are the low-resolution HRNet branches), its BN parameters are slices."""
+    Cin = x.shape[-1]
+    Cout = dy.shape[-1]
+    dw = torch.empty((Cout, Cin, ksize, ksize), dtype=torch.float32, device=x.device)
+    c0 = 0
+    for cw in chunks:
+        xs = x[..., c0:c0 + cw].contiguous()
+        sl = slice(c0, c0 + cw)
+        dws = conv2d_wgrad_tc_fused(xs, dy, ksize, mean=None if mean is None else mean[sl],
+                                    scale=None if scale is None else scale[sl],
+                                    shift=None if shift is None else shift[sl], relu=relu, passes=passes)
+        dw[:, sl] = dws
+        c0 += cw
+    return dw
+
+
 def bn_stats(x):
     C = x.shape[-1]
     P = x.numel() // C
@@ -394,7 +424,8 @@ def bn_bwd(da, x, mean, invstd, scale, shift, gamma, relu, accumulate_into=None,
     sums = bn_bwd_reduce(da, x, mean, invstd, scale, shift, relu)
     apply_sums = sums if sync_mean is None else sync_mean(sums)
     dx = accumulate_into if accumulate_into is not None else torch.empty_like(x)
-    if want_dx_sum and accumulate_into is None and FUSED_REDUCE and BN_APPLY_SUM and C % 4 == 0:
+    if (want_dx_sum and accumulate_into is None and FUSED_REDUCE and (BN_APPLY_SUM or want_dx_sum == "force")
+            and C % 4 == 0):
         # the same pass also yields sum_pixels(dx) per channel and the operand scale of dx: what channel_sum(dx,
         # want_amax=True) would compute for the bias gradient / 3xFP16 data gradient of the conv that produced x
         dx_sum = torch.empty(C, dtype=torch.float32, device=x.device)

@@ -80,7 +80,9 @@ def test_kernel_shape_planners_on_cpu():
         assert lib.fpd_conv2d_wgrad_tc3_supported(hw, hw, 64, 64, 3) == 1
     assert lib.fpd_conv2d_wgrad_tc3_supported(64, 48, 64, 32, 3) == 1
     assert lib.fpd_conv2d_wgrad_tc3_supported(4, 4, 64, 64, 3) == 0            # a K step must be 8 pixels along w
-    assert lib.fpd_conv2d_wgrad_tc3_supported(64, 64, 32, 32, 3) == 0          # M = Cin must be 64 or 128
+    assert lib.fpd_conv2d_wgrad_tc3_supported(64, 64, 32, 32, 3) == 1          # Cin = 32: two taps per M = 64 instruction
+    assert lib.fpd_conv2d_wgrad_tc3_supported(64, 64, 32, 128, 3) == 0         # ... needs 5 x Cout <= 512 TMEM columns
+    assert lib.fpd_conv2d_wgrad_tc3_supported(64, 64, 16, 32, 3) == 0          # M = Cin must be 32, 64 or 128
     assert lib.fpd_conv2d_wgrad_tc3_supported(64, 64, 64, 64, 1) == 0          # 1x1: wgrad_tc2
     assert lib.fpd_conv2d_wgrad_tc3_supported(32, 32, 128, 128, 3) == 0        # one stage only: wgrad_tc2
     # workspace of the dispatching entry point covers whichever kernel runs

@@ -222,7 +222,9 @@ WGRAD_TC_SHAPES = [
     (3, 8, 8, 128, 64, 1),      # ragged batch tile
     (2, 128, 128, 32, 32, 3),   # layer1 conv2 (4 taps stacked)
     (1, 32, 32, 128, 128, 3),
-    (2, 64, 48, 32, 32, 3),
+    (2, 64, 48, 32, 32, 3),     # HRNet branch 0 (wgrad_tc3 pair mode: two taps per M = 64 MMA)
+    (2, 64, 48, 32, 64, 3),     # HRNet fuse down path in stride-1 form
+    (4, 32, 24, 32, 96, 3),
     (2, 32, 32, 128, 256, 1),
     (2, 64, 64, 128, 16, 1),    # score conv (dY has 16 channels: M tile completed by TMA zero fill)
     (2, 64, 64, 16, 128, 1),    # score_ conv
@@ -625,7 +627,7 @@ def test_conv2d_tc_h_epilogue_batchnorm_statistics(shape, f16, with_pivot):
     o = ops()
     o.CONV_STATS = "1"      # off by default (measured neutral on the bench step): the kernel variant is tested regardless
     nblk = o.conv2d_tc_h_stats_blocks(B, H, W, Cin, Cout, k, f16)
-    o.CONV_STATS = os.environ.get("FPD_CONV_STATS", "0").lower()
+    o.CONV_STATS = os.environ.get("FPD_CONV_STATS", "3x3").lower()
     if nblk == 0:
         pytest.skip("shape does not carry epilogue statistics")
     g = torch.Generator(device="cuda").manual_seed(77)
