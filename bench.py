@@ -534,8 +534,7 @@ def run_b200(args, rank, local_rank, world):
     e2e_value = world * B / (ms_e2e / 1000.0)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, dist)
         return
 
     peaks, peak_src = measured_peaks()
@@ -584,8 +583,23 @@ def run_b200(args, rank, local_rank, world):
         except Exception as exc:
             line["cpu_baseline"] = {"error": repr(exc)}
     print(json.dumps(line), flush=True)
+    _finish(world, dist)
+
+
+def _finish(world, dist):
+    """Leave together and for sure: a last barrier (the other ranks wait for rank 0's side measurements), the process group
+    torn down while every rank is still alive, then a hard exit -- interpreter finalisation with live CUDA graphs / NCCL
+    communicators has been seen to hang a rank for minutes after its work was done (r2 2-GPU run), which a driver that
+    waits for torchrun to exit would count as the job's time."""
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:
+            pass
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # launch-weighted roofline fraction of conv_tc_h_kernel over one whole step (all its launches): conv FLOPs it executes

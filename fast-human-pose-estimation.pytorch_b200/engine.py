@@ -133,10 +133,13 @@ class PreparedWeights:
     [tap][O][I] hi/lo (+ flipped/transposed for dgrad). Forward operands are __half pairs (3xFP16, csrc/conv_tc5.cu)
     where that kernel takes the shape, fp32 containers holding tf32 values otherwise."""
 
-    def __init__(self, passes):
+    def __init__(self, passes, scale_without_bias=False):
         self.split = passes == 3
         self._fwd = {}
         self._dgrad = {}
+        # bias-free convolutions get the operand scale of dY from the BatchNorm-backward pass (Engine.force_apply_sum):
+        # their 3xFP16 data-gradient weights can then come out of the same launch as the forward ones
+        self.scale_without_bias = scale_without_bias
 
     def fwd(self, c, H, W, also_dgrad=False):
         """-> (w_hi, w_lo, use_h): use_h selects ops.conv2d_tc_h (generation-5 kernel) over the TS kernel.
@@ -154,8 +157,8 @@ class PreparedWeights:
             w2[:, :c.cin * c.k * c.k, 0, 0] = w.permute(0, 2, 3, 1).reshape(c.cout, -1)
             w, k, cin = w2, 1, kpad
         if FUSED_FWD and self.split and ops.CONV_F16 and ops.conv2d_tc_h_supported(cin, c.cout, k, H, W, True):
-            if (also_dgrad and not kpad and FUSED_DGRAD and ops.CONV_F16_DGRAD and ops.FUSED_REDUCE and c.bias is not None
-                    and c.tc_dgrad and ops.conv2d_tc_h_supported(c.cout, c.cin, c.k, H, W, True)):
+            if (also_dgrad and not kpad and FUSED_DGRAD and ops.CONV_F16_DGRAD and ops.FUSED_REDUCE
+                    and (c.bias is not None or self.scale_without_bias) and c.tc_dgrad and ops.conv2d_tc_h_supported(c.cout, c.cin, c.k, H, W, True)):
                 (hi, lo), (dhi, dlo) = ops.weight_prep_f16_both(w)
                 self._dgrad[c.name] = (dhi, dlo, True)
             else:
@@ -647,13 +650,13 @@ class Engine:
         ctx.passes = precision_passes()
         ctx.tape = [] if record_tape else None
         if training:
-            ctx.weights = PreparedWeights(ctx.passes)
+            ctx.weights = PreparedWeights(ctx.passes, self.force_apply_sum)
             ctx.affine = None
             self.invalidate_eval_cache()      # this forward rewrites the running statistics on the device
         else:
             w, affine = self._eval_prepared()
             if record_tape:
-                w = PreparedWeights(ctx.passes)
+                w = PreparedWeights(ctx.passes, self.force_apply_sum)
             ctx.weights, ctx.affine = w, affine
         img = img_nchw if (img_nchw.is_contiguous() and img_nchw.dtype == torch.float32) else img_nchw.contiguous().float()
         outs = self.run_network(ctx, img)
