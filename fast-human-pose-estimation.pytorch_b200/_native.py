@@ -23,15 +23,9 @@ _SIGNATURES = {
     "fpd_version": (c_int, []),
     "fpd_sm_count": (c_int, []),
     "fpd_launch_count": (ctypes.c_longlong, []),
-    "fpd_conv2d_tc_supported": (c_int, [c_int, c_int, c_int]),
-    "fpd_conv2d_tc": (c_int, [P, P, P, P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, P]),
-    "fpd_conv2d_tc_fused": (c_int, [P, P, P, P, c_int, P, P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int,
-                                    c_int, P]),
     "fpd_conv2d_tc_ts_supported": (c_int, [c_int, c_int, c_int]),
     "fpd_conv2d_tc_ts": (c_int, [P, P, P, P, c_int, P, P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int,
                                  c_int, P]),
-    "fpd_conv2d_tc_g": (c_int, [P, P, P, P, c_int, P, P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int,
-                                c_int, P]),
     "fpd_conv2d_tc_h_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "fpd_conv2d_tc_h": (c_int, [P, P, P, P, c_int, P, P, c_int, P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int,
                                 c_int, P]),
@@ -48,7 +42,6 @@ _SIGNATURES = {
     "fpd_conv2d_wgrad_tc3_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "fpd_conv2d_wgrad_tc_supported": (c_int, [c_int, c_int, c_int]),
     "fpd_conv2d_wgrad_tc_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
-    "fpd_conv2d_wgrad_tc": (c_int, [P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),
     "fpd_conv2d_wgrad_tc_fused": (c_int, [P, P, P, P, c_int, P, c_int, P, c_float, c_int, c_int, c_int, c_int, c_int,
                                           c_int, P, c_size_t, P]),
     "fpd_conv2d_simt_fwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),

@@ -14,7 +14,7 @@ OUT = os.path.join(HERE, "libfpd_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
-SOURCES = ["api.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "conv_tc4.cu", "conv_tc5.cu", "wgrad_tc.cu", "wgrad_tc2.cu", "wgrad_tc3.cu", "conv_simt.cu", "elementwise.cu", "loss.cu", "decode.cu", "nms.cu",
+SOURCES = ["api.cu", "conv_tc3.cu", "conv_tc5.cu", "wgrad_tc2.cu", "wgrad_tc3.cu", "conv_simt.cu", "elementwise.cu", "loss.cu", "decode.cu", "nms.cu",
            "adam.cu"]
 
 

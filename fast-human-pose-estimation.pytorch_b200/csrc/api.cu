@@ -87,22 +87,8 @@ int fpd_version(void) { return 100; }
 int fpd_sm_count(void) { return device_sm_count(); }
 long long fpd_launch_count(void) { return fpd::g_launches.load(std::memory_order_relaxed); }
 
-int fpd_conv2d_tc_supported(int Cin, int Cout, int ksize) { return conv_tc_supported(Cin, Cout, ksize) ? 1 : 0; }
 
-int fpd_conv2d_tc(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, const float* bias,
-                  const float* residual, const float* relu_mask, float* y, float out_scale, int B, int H, int W,
-                  int Cin, int Cout, int ksize, fpd_stream_t stream) {
-  return conv_tc_launch(a_hi, a_lo, w_hi, w_lo, bias, residual, relu_mask, y, out_scale, B, H, W, Cin, Cout, ksize,
-                        device_sm_count(), S(stream));
-}
 
-int fpd_conv2d_tc_fused(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
-                        int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
-                        const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
-                        int ksize, fpd_stream_t stream) {
-  return conv_tc_fused_launch(x, pre_mean, pre_scale, pre_shift, pre_relu, w_hi, w_lo, bias, residual, relu_mask, y,
-                              out_scale, B, H, W, Cin, Cout, ksize, device_sm_count(), S(stream));
-}
 
 int fpd_conv2d_tc_ts_supported(int Cin, int Cout, int ksize) { return conv_tc_ts_supported(Cin, Cout, ksize) ? 1 : 0; }
 
@@ -114,13 +100,6 @@ int fpd_conv2d_tc_ts(const float* x, const float* pre_mean, const float* pre_sca
                            out_scale, B, H, W, Cin, Cout, ksize, device_sm_count(), S(stream));
 }
 
-int fpd_conv2d_tc_g(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
-                    int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
-                    const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
-                    int ksize, fpd_stream_t stream) {
-  return conv_tc_g_launch(x, pre_mean, pre_scale, pre_shift, pre_relu, w_hi, w_lo, bias, residual, relu_mask, y,
-                          out_scale, B, H, W, Cin, Cout, ksize, device_sm_count(), S(stream));
-}
 
 int fpd_conv2d_tc_h_supported(int Cin, int Cout, int ksize, int H, int W, int f16) {
   return conv_tc_h_supported(Cin, Cout, ksize, H, W, f16) ? 1 : 0;
@@ -198,12 +177,6 @@ size_t fpd_conv2d_wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cou
   const size_t b = wgrad_tc3_supported(H, W, Cin, Cout, ksize)
                        ? wgrad_tc3_workspace_bytes(B, H, W, Cin, Cout, device_sm_count()) : 0;
   return a > b ? a : b;
-}
-int fpd_conv2d_wgrad_tc(const float* a_hi, const float* a_lo, const float* dy_hi, const float* dy_lo,
-                        float* dw_oihw, float scale, int B, int H, int W, int Cin, int Cout, int ksize,
-                        void* workspace, size_t workspace_bytes, fpd_stream_t stream) {
-  return wgrad_tc_launch(a_hi, a_lo, dy_hi, dy_lo, dw_oihw, scale, B, H, W, Cin, Cout, ksize, workspace,
-                         workspace_bytes, device_sm_count(), S(stream));
 }
 
 int fpd_conv2d_wgrad_tc_fused(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,

@@ -7,31 +7,13 @@
 
 namespace fpd {
 
-// ---- conv_tc.cu : tcgen05 implicit GEMM (1x1 / 3x3 stride 1) ----
-bool conv_tc_supported(int Cin, int Cout, int ksize);
-int conv_tc_launch(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, const float* bias,
-                   const float* residual, const float* relu_mask, float* y, float out_scale, int B, int H, int W,
-                   int Cin, int Cout, int ksize, int num_sms, cudaStream_t stream);
-
-// ---- conv_tc2.cu : same GEMM with BN-apply + ReLU + tf32 split fused into the pipeline (raw fp32 x in) ----
-int conv_tc_fused_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
-                         int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
-                         const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
-                         int ksize, int num_sms, cudaStream_t stream);
-
 // ---- conv_tc3.cu : fused operand transform with the A operand in tensor memory (TS-mode MMA) ----
-bool conv_tc_ts_supported(int Cin, int Cout, int ksize);   // wider than conv_tc_supported: Cout up to 1024 in slices
+bool conv_tc_ts_supported(int Cin, int Cout, int ksize);   // Cout up to 1024 in slices of <= 128 columns
 int conv_tc_ts_slice(int Cout);
 int conv_tc_ts_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                       int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
                       const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
                       int ksize, int num_sms, cudaStream_t stream);
-
-// ---- conv_tc4.cu : fused transform, A operand global -> registers -> TMEM (no shared-memory traffic for A) ----
-int conv_tc_g_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
-                     int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
-                     const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
-                     int ksize, int num_sms, cudaStream_t stream);
 
 // ---- conv_tc5.cu : halo-tile reuse (3x3: one fetch + one transform per channel block, nine shifted smem->TMEM copies)
 //      and optional 3xFP16 operands (f16 = 1: w_hi / w_lo are __half [tap][Cout][Cin] from weight_prep_f16, pre-scaled
@@ -48,14 +30,10 @@ int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_sca
 // stat_part[blocks][Cout][2] (0: this shape cannot carry the statistics, e.g. Cout > 256)
 int conv_tc_h_stats_grid(int B, int H, int W, int Cin, int Cout, int ksize, int f16, int num_sms);
 
-// ---- wgrad_tc.cu : tcgen05 weight-gradient GEMM (K = pixels) ----
+// ---- wgrad_tc2.cu : tcgen05 weight-gradient GEMM (K = pixels) reading RAW x and dY; BN-apply + ReLU + tf32 split fused
+//      into the pipeline ----
 bool wgrad_tc_supported(int Cin, int Cout, int ksize);
 size_t wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize, int num_sms);
-int wgrad_tc_launch(const float* a_hi, const float* a_lo, const float* dy_hi, const float* dy_lo, float* dw_oihw,
-                    float scale, int B, int H, int W, int Cin, int Cout, int ksize, void* workspace,
-                    size_t workspace_bytes, int num_sms, cudaStream_t stream);
-
-// ---- wgrad_tc2.cu : same GEMM reading RAW x and dY; BN-apply + ReLU + tf32 split fused into the pipeline ----
 int wgrad_tc_fused_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                           int pre_relu, const float* dy, int passes, float* dw_oihw, float scale, int B, int H, int W,
                           int Cin, int Cout, int ksize, void* workspace, size_t workspace_bytes, int num_sms,

@@ -1,14 +1,9 @@
 // wgrad_tc2.cu -- convolution weight gradient on the sm_100a tensor cores, operand preparation fused in.
 //
-// Same GEMM / tiling / split-K scheme as wgrad_tc.cu, but both operands are read RAW (fp32 x and dY, one TMA box
-// each instead of hi/lo pairs) and eight transform warps produce, in shared memory,
+// Both operands are read RAW (fp32 x and dY, one TMA box each) and eight transform warps produce, in shared memory,
 //     a = relu?((x - mean) * scale + shift)  (zeroed at the 3x3 padding positions)  ->  (a_hi, a_lo)
 //     dY                                                                            ->  (g_hi, g_lo)
 // before the MMA warp consumes the stage -- the backward pass then needs no separate operand-split passes at all.
-// (Everything below this banner that is not about the transform is documented in wgrad_tc.cu.)
-//
-// [wgrad_tc.cu header follows]
-// wgrad_tc.cu -- convolution weight gradient on the sm_100a tensor cores.
 //
 //   dW[co][ci][tap] = scale * sum_{pixels p} dY[p][co] * A[p (+) tap][ci]        (stride 1, "same" padding)
 //
@@ -386,6 +381,16 @@ int choose_splits(int groups, int num_ktiles, int num_sms) {
 
 }  // namespace
 
+bool wgrad_tc_supported(int Cin, int Cout, int ksize) { return make_plan(Cin, Cout, ksize).ok; }
+
+size_t wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize, int num_sms) {
+  Plan pl = make_plan(Cin, Cout, ksize);
+  if (!pl.ok) return 0;
+  const int bw = pow2_div(W, kKp), bh = pow2_div(H, kKp / bw), bn = kKp / (bw * bh);
+  const int num_ktiles = (W / bw) * (H / bh) * ((B + bn - 1) / bn);
+  const int splits = choose_splits(pl.groups, num_ktiles, num_sms);
+  return (size_t)splits * pl.groups * 128 * pl.N * sizeof(float);
+}
 
 int wgrad_tc_fused_launch(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                           int pre_relu, const float* dy, int passes, float* dw_oihw, float scale, int B, int H, int W,

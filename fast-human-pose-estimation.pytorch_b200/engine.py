@@ -15,12 +15,9 @@ import torch
 from . import ops
 
 
-# conv(relu(bn(x))) with the operand transform inside the tensor-core kernel (csrc/conv_tc2.cu); FPD_FUSED=0 falls back to
-# the two-kernel form (affine_act_split + conv_tc), kept for A/B measurements.
-_FUSED = os.environ.get("FPD_FUSED", "1").lower()
-FUSED_FWD = _FUSED in ("1", "all", "fwd")     # forward convs (student + teacher)
-FUSED_DGRAD = _FUSED in ("1", "all", "bwd", "dgrad")
-FUSED_WGRAD = _FUSED in ("1", "all", "bwd", "wgrad")
+# conv(relu(bn(x))): the operand transform (BN-apply + ReLU + hi/lo split) always happens inside the tensor-core kernels
+# (csrc/conv_tc5.cu, conv_tc3.cu, wgrad_tc2.cu, wgrad_tc3.cu); the round-1 two-kernel forms (pre-split operands in HBM)
+# and their A/B switches were removed in round 2.
 # forward: run each hourglass level's skip branch on a side stream (see Engine.hourglass)
 FORK_UP1 = os.environ.get("FPD_FORK_UP1", "1") != "0"
 # opt-in SyncBN over the default process group (see parallel.py); the reference's semantics are per-replica statistics
@@ -106,13 +103,11 @@ class ConvRef:
 
     @property
     def tc_fwd(self):
-        return self.s1 and self.pad == self.k // 2 and ops.conv2d_tc_supported(self.cin, self.cout, self.k,
-                                                                                fused=FUSED_FWD)
+        return self.s1 and self.pad == self.k // 2 and ops.conv2d_tc_supported(self.cin, self.cout, self.k)
 
     @property
     def tc_dgrad(self):
-        return self.s1 and self.pad == self.k // 2 and ops.conv2d_tc_supported(self.cout, self.cin, self.k,
-                                                                                fused=FUSED_DGRAD)
+        return self.s1 and self.pad == self.k // 2 and ops.conv2d_tc_supported(self.cout, self.cin, self.k)
 
     @property
     def tc_wgrad(self):
@@ -156,8 +151,8 @@ class PreparedWeights:
             w2 = torch.zeros((c.cout, kpad, 1, 1), dtype=torch.float32, device=w.device)
             w2[:, :c.cin * c.k * c.k, 0, 0] = w.permute(0, 2, 3, 1).reshape(c.cout, -1)
             w, k, cin = w2, 1, kpad
-        if FUSED_FWD and self.split and ops.CONV_F16 and ops.conv2d_tc_h_supported(cin, c.cout, k, H, W, True):
-            if (also_dgrad and not kpad and FUSED_DGRAD and ops.CONV_F16_DGRAD and ops.FUSED_REDUCE
+        if self.split and ops.CONV_F16 and ops.conv2d_tc_h_supported(cin, c.cout, k, H, W, True):
+            if (also_dgrad and not kpad and ops.CONV_F16_DGRAD and ops.FUSED_REDUCE
                     and (c.bias is not None or self.scale_without_bias) and c.tc_dgrad and ops.conv2d_tc_h_supported(c.cout, c.cin, c.k, H, W, True)):
                 (hi, lo), (dhi, dlo) = ops.weight_prep_f16_both(w)
                 self._dgrad[c.name] = (dhi, dlo, True)
@@ -166,7 +161,7 @@ class PreparedWeights:
             e = (hi, lo, True)
         else:
             hi, lo = ops.weight_prep(w, for_dgrad=False, split=self.split)
-            e = (hi, lo, FUSED_FWD and ops.conv2d_tc_h_supported(cin, c.cout, k, H, W, False))
+            e = (hi, lo, ops.conv2d_tc_h_supported(cin, c.cout, k, H, W, False))
         self._fwd[c.name] = e
         return e
 
@@ -176,13 +171,13 @@ class PreparedWeights:
         if e is not None and e[0].dtype == torch.float16 and not f16_ok:
             e = None   # prepared together with the forward form, but no operand scale for dY: use the 3xTF32 form
         if e is None:
-            if (f16_ok and FUSED_DGRAD and self.split and ops.CONV_F16_DGRAD
+            if (f16_ok and self.split and ops.CONV_F16_DGRAD
                     and ops.conv2d_tc_h_supported(c.cout, c.cin, c.k, H, W, True)):
                 hi, lo = ops.weight_prep_f16(c.weight.detach(), for_dgrad=True, split=True)
                 e = (hi, lo, True)
             else:
                 hi, lo = ops.weight_prep(c.weight.detach(), for_dgrad=True, split=self.split)
-                e = (hi, lo, FUSED_DGRAD and ops.conv2d_tc_h_supported(c.cout, c.cin, c.k, H, W, False))
+                e = (hi, lo, ops.conv2d_tc_h_supported(c.cout, c.cin, c.k, H, W, False))
             self._dgrad[c.name] = e
         return e
 
@@ -349,7 +344,6 @@ class Engine:
                     ctx._in_s1 = False
                 return self.subsample2(ctx, full)
         s1_ok = c.stride == 1 or getattr(ctx, "_in_s1", False)
-        split = ctx.passes == 3
         scale = shift = mean = None
         aff = None
         if bn_name is not None:
@@ -357,7 +351,6 @@ class Engine:
             scale, shift, mean = aff[0], aff[1], aff[2]
         bias = c.bias.detach() if c.bias is not None else None
         res = residual.data if residual is not None else None
-        a_hi = a_lo = None
         kpad = c.im2col_kpad if bn_name is None else 0
         if kpad:
             key = (x.data.data_ptr(), tuple(x.data.shape), c.k, c.stride, c.pad, kpad)
@@ -391,7 +384,7 @@ class Engine:
             w_hi, w_lo, use_h = ctx.weights.fwd(c, x.data.shape[1], x.data.shape[2],
                                                 also_dgrad=ctx.tape is not None and need_dx)
             stat_sums = None
-            if FUSED_FWD and use_h and out_bn and ctx.training and ctx.sync is None:
+            if use_h and out_bn and ctx.training and ctx.sync is None:
                 Bn, Hn, Wn = x.data.shape[0], x.data.shape[1], x.data.shape[2]
                 nblk = ops.conv2d_tc_h_stats_blocks(Bn, Hn, Wn, c.cin, c.cout, c.k, w_hi.dtype == torch.float16)
                 if nblk > 0:
@@ -402,14 +395,11 @@ class Engine:
             if stat_sums is not None:
                 y = ops.conv2d_tc_h(x.data, w_hi, w_lo, c.k, mean=mean, scale=scale, shift=shift, relu=relu, bias=bias,
                                     residual=res, stats_part=stat_sums[0], stats_pivot=stat_sums[2])
-            elif FUSED_FWD:
+            else:
                 # BN-apply + ReLU + operand split happen inside the conv kernel (no separate HBM pass)
                 conv_fn = ops.conv2d_tc_h if use_h else ops.conv2d_tc_fused
                 y = conv_fn(x.data, w_hi, w_lo, c.k, mean=mean, scale=scale, shift=shift, relu=relu, bias=bias,
                             residual=res)
-            else:
-                a_hi, a_lo = ops.affine_act_split(x.data, scale, shift, relu, split=split, mean=mean)
-                y = ops.conv2d_tc(a_hi, a_lo, w_hi, w_lo, c.k, bias=bias, residual=res)
         else:
             a = ops.affine_act(x.data, scale, shift, relu, mean=mean) if bn_name is not None else x.data
             y = ops.conv2d_simt_fwd(a, c.weight.detach(), bias=bias, residual=res, stride=c.stride, pad=c.pad)
@@ -421,12 +411,10 @@ class Engine:
         in_s1 = c.as_s1 and s1_ok            # stride-2 conv running as stride 1 + pick: dY arrives zero-upsampled
         stride_eff = 1 if in_s1 else c.stride
         wgrad_chunks = None                  # too wide for one tensor-core wgrad launch: one launch per channel chunk
-        if (ctx.tape is not None and not tc_wgrad and s1_ok and FUSED_WGRAD and c.pad == c.k // 2
+        if (ctx.tape is not None and not tc_wgrad and s1_ok and c.pad == c.k // 2
                 and (bn_name is not None or not c.im2col_kpad)):
             wgrad_chunks = ops.wgrad_channel_chunks(c.cin, c.cout, c.k)
         if ctx.tape is not None:
-            keep = [a_hi, a_lo] if tc_wgrad else [None, None]
-
             def bwd():
                 dy = out.grad
                 if dy is None:
@@ -443,11 +431,8 @@ class Engine:
                 elif c.bias is not None:
                     # bias gradient; the same pass over dY yields the power-of-two scale of the 3xFP16 data gradient
                     ctx.pgrads[c.bias], dy_scale = ops.channel_sum(dy, want_amax=True)
-                dy_hi = dy_lo = None
-                if (tc_wgrad and not FUSED_WGRAD) or (need_dx and tc_dgrad and not FUSED_DGRAD):
-                    dy_hi, dy_lo = ops.affine_act_split(dy, split=split)
                 # ---- weight gradient
-                if tc_wgrad and FUSED_WGRAD and ctx.wgrad_stream is not None:
+                if tc_wgrad and ctx.wgrad_stream is not None:
                     # dW (and the bias gradient) are leaves of the backward graph: compute them on a side stream so they
                     # fill the SMs that the small-grid kernels of the critical dgrad/BN chain leave idle
                     main = torch.cuda.current_stream()
@@ -458,17 +443,12 @@ class Engine:
                         ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc_fused(x.data, dy, c.k, mean=mean, scale=scale,
                                                                          shift=shift, relu=relu, passes=ctx.passes)
                     ctx.keepalive.append(dy)     # dy must outlive the side-stream kernel (released after the join)
-                elif tc_wgrad and FUSED_WGRAD:
+                elif tc_wgrad:
                     ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc_fused(x.data, dy, c.k, mean=mean, scale=scale, shift=shift,
                                                                      relu=relu, passes=ctx.passes)
                 elif wgrad_chunks is not None:
                     ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc_chunked(x.data, dy, c.k, wgrad_chunks, mean=mean, scale=scale,
                                                                        shift=shift, relu=relu, passes=ctx.passes)
-                elif tc_wgrad:
-                    if keep[0] is None:  # fused forward did not materialise the operand pair: make it now
-                        keep[0], keep[1] = ops.affine_act_split(x.data, scale, shift, relu, split=split, mean=mean)
-                    ctx.pgrads[c.weight] = ops.conv2d_wgrad_tc(keep[0], keep[1], dy_hi, dy_lo, c.k)
-                    keep[0] = keep[1] = None
                 else:
                     a_full = (ops.affine_act(x.data, scale, shift, relu, mean=mean) if bn_name is not None
                               else x.data)
@@ -481,14 +461,11 @@ class Engine:
                 # ---- data gradient w.r.t. the conv input a = act(bn(x))
                 if tc_dgrad:
                     wd_hi, wd_lo, use_h = ctx.weights.dgrad(c, dy.shape[1], dy.shape[2], f16_ok=dy_scale is not None)
-                    if FUSED_DGRAD:
-                        if use_h:
-                            da = ops.conv2d_tc_h(dy, wd_hi, wd_lo, c.k,
-                                                 in_scale=dy_scale if wd_hi.dtype == torch.float16 else None)
-                        else:
-                            da = ops.conv2d_tc_fused(dy, wd_hi, wd_lo, c.k)
+                    if use_h:
+                        da = ops.conv2d_tc_h(dy, wd_hi, wd_lo, c.k,
+                                             in_scale=dy_scale if wd_hi.dtype == torch.float16 else None)
                     else:
-                        da = ops.conv2d_tc(dy_hi, dy_lo, wd_hi, wd_lo, c.k)
+                        da = ops.conv2d_tc_fused(dy, wd_hi, wd_lo, c.k)
                 else:
                     da = ops.conv2d_simt_dgrad(dy, c.weight.detach(), x.data.shape[1:3], stride=stride_eff, pad=c.pad)
                 if bn_name is not None:

@@ -63,11 +63,9 @@ def _counter(device):
 FUSED_REDUCE = os.environ.get("FPD_FUSED_REDUCE", "1") != "0"   # single-launch reductions (A/B switch)
 
 
-def conv2d_tc_supported(cin, cout, k, fused=False):
-    """fused=True asks about the kernel conv2d_tc_fused dispatches to (the TS kernel takes Cout > 256 in slices)."""
-    if fused and CONV_FUSED_IMPL == "ts":
-        return bool(N.lib().fpd_conv2d_tc_ts_supported(cin, cout, k))
-    return bool(N.lib().fpd_conv2d_tc_supported(cin, cout, k))
+def conv2d_tc_supported(cin, cout, k, fused=True):
+    """Does a tensor-core convolution kernel take these channel counts (the TS kernel takes Cout > 256 in slices)?"""
+    return bool(N.lib().fpd_conv2d_tc_ts_supported(cin, cout, k))
 
 
 def weight_prep(w_oihw, for_dgrad=False, split=True):
@@ -140,28 +138,16 @@ def im2col(x, k, stride, pad, kpad, out=None):
     return cols
 
 
-def conv2d_tc(a_hi, a_lo, w_hi, w_lo, ksize, bias=None, residual=None, relu_mask=None, out=None, out_scale=1.0):
-    B, H, W, Cin = a_hi.shape
-    Cout = w_hi.shape[1]
-    y = out if out is not None else torch.empty((B, H, W, Cout), dtype=torch.float32, device=a_hi.device)
-    N.check(N.lib().fpd_conv2d_tc(_p(a_hi), _p(a_lo), _p(w_hi), _p(w_lo), _p(bias), _p(residual), _p(relu_mask), _p(y),
-                                  float(out_scale), B, H, W, Cin, Cout, ksize, _stream()), "conv2d_tc")
-    return y
-
-
-CONV_FUSED_IMPL = os.environ.get("FPD_CONV_IMPL", "ts").lower()   # "ts": A operand in TMEM (conv_tc3.cu); "ss": conv_tc2.cu
-
-
 def conv2d_tc_fused(x, w_hi, w_lo, ksize, mean=None, scale=None, shift=None, relu=False, bias=None, residual=None,
-                    relu_mask=None, out=None, out_scale=1.0, impl=None):
-    """y = conv(relu?((x-mean)*scale+shift)) with the operand transform done inside the kernel (raw fp32 x in)."""
+                    relu_mask=None, out=None, out_scale=1.0):
+    """y = conv(relu?((x-mean)*scale+shift)) on the TS kernel (csrc/conv_tc3.cu: per-tap TMA, operand transform -> TMEM,
+    3xTF32) -- the fallback for the shapes the generation-5 kernel (conv2d_tc_h) declines."""
     B, H, W, Cin = x.shape
     Cout = w_hi.shape[1]
     y = out if out is not None else torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
-    which = impl or CONV_FUSED_IMPL
-    fn = {"ts": N.lib().fpd_conv2d_tc_ts, "g": N.lib().fpd_conv2d_tc_g, "ss": N.lib().fpd_conv2d_tc_fused}[which]
-    N.check(fn(_p(x), _p(mean), _p(scale), _p(shift), int(relu), _p(w_hi), _p(w_lo), _p(bias), _p(residual),
-               _p(relu_mask), _p(y), float(out_scale), B, H, W, Cin, Cout, ksize, _stream()), "conv2d_tc_fused")
+    N.check(N.lib().fpd_conv2d_tc_ts(_p(x), _p(mean), _p(scale), _p(shift), int(relu), _p(w_hi), _p(w_lo), _p(bias),
+                                     _p(residual), _p(relu_mask), _p(y), float(out_scale), B, H, W, Cin, Cout, ksize,
+                                     _stream()), "conv2d_tc_ts")
     return y
 
 
@@ -280,17 +266,6 @@ def conv2d_simt_wgrad(x, dy, k, stride=1, pad=0, scale=1.0, out=None):
 
 def conv2d_wgrad_tc_supported(cin, cout, k):
     return bool(N.lib().fpd_conv2d_wgrad_tc_supported(cin, cout, k))
-
-
-def conv2d_wgrad_tc(a_hi, a_lo, dy_hi, dy_lo, ksize, scale=1.0, out=None):
-    B, H, W, Cin = a_hi.shape
-    Cout = dy_hi.shape[-1]
-    dw = out if out is not None else torch.empty((Cout, Cin, ksize, ksize), dtype=torch.float32, device=a_hi.device)
-    nb = N.lib().fpd_conv2d_wgrad_tc_workspace_bytes(B, H, W, Cin, Cout, ksize)
-    ws = _ws.get(nb, a_hi.device)
-    N.check(N.lib().fpd_conv2d_wgrad_tc(_p(a_hi), _p(a_lo), _p(dy_hi), _p(dy_lo), _p(dw), float(scale), B, H, W, Cin,
-                                        Cout, ksize, _p(ws), ws.numel(), _stream()), "conv2d_wgrad_tc")
-    return dw
 
 
 def conv2d_wgrad_tc_fused(x, dy, ksize, mean=None, scale=None, shift=None, relu=False, passes=3, out_scale=1.0,

@@ -47,45 +47,24 @@ long long fpd_launch_count(void);
  * lib/models/pose_hrnet.py:23-25 (conv3x3), :33-37,66-74.
  * ------------------------------------------------------------------------------------------------- */
 
-/* 1 if (Cin, Cout, ksize) is handled by the tcgen05 kernels (ksize in {1,3}, stride 1, "same" pad). */
-int fpd_conv2d_tc_supported(int Cin, int Cout, int ksize);
-
-/* Tensor-core implicit GEMM, forward or data-gradient (dgrad = same call on dY with weights prepared
- * by fpd_weight_prep(for_dgrad=1)).
- *   y[B,H,W,Cout] = out_scale * conv(a, w) (+ bias[Cout]) (+ residual[B,H,W,Cout]); if relu_mask is
- *   given (same shape as y) elements with relu_mask <= 0 are written as 0 (ReLU backward fused).
- *   a_hi/a_lo : NHWC tf32 hi/lo operand pair from fpd_affine_act_split (a_lo NULL => single-pass TF32,
- *               then w_lo must be NULL too; both non-NULL => 3xTF32, fp32-grade accuracy)
- *   w_hi/w_lo : [ksize*ksize][Cout][Cin] from fpd_weight_prep */
-int fpd_conv2d_tc(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, const float* bias,
-                  const float* residual, const float* relu_mask, float* y, float out_scale, int B, int H, int W,
-                  int Cin, int Cout, int ksize, fpd_stream_t stream);
-
-/* Same convolution with the operand preparation fused in: x is the RAW fp32 NHWC activation and the kernel applies
- * a = relu?((x - pre_mean) * pre_scale + pre_shift) (pre_scale/pre_shift NULL = identity, pre_mean NULL = 0) and the
- * tf32 hi/lo split in shared memory -- i.e. conv(relu(bn(x))) of lib/models/hourglass.py:34-44 in one kernel.
- * w_lo NULL => single-pass TF32. Other arguments as fpd_conv2d_tc. */
-int fpd_conv2d_tc_fused(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
-                        int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
-                        const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
-                        int ksize, fpd_stream_t stream);
-
-/* Same contract as fpd_conv2d_tc_fused, but the prepared A tiles are written to tensor memory and the MMAs run in
- * TS mode (A from TMEM, B from shared memory): removes the shared-memory-bandwidth bound of the SS form for Cout <= 128. */
+/* Tensor-core implicit GEMM with the operand preparation fused in, forward or data-gradient (dgrad = same call on dY with
+ * weights prepared by fpd_weight_prep(for_dgrad=1)): x is the RAW fp32 NHWC activation and the kernel applies
+ * a = relu?((x - pre_mean) * pre_scale + pre_shift) (pre_scale/pre_shift NULL = identity, pre_mean NULL = 0) and the tf32
+ * hi/lo split on chip -- i.e. conv(relu(bn(x))) of lib/models/hourglass.py:34-44 in one kernel.
+ *   y[B,H,W,Cout] = out_scale * conv(a, w) (+ bias[Cout]) (+ residual[B,H,W,Cout]); if relu_mask is given (same shape as
+ *   y) elements with relu_mask <= 0 are written as 0 (ReLU backward fused).
+ *   w_hi/w_lo : [ksize*ksize][Cout][Cin] fp32 containers holding tf32 values from fpd_weight_prep (w_lo NULL => single-pass
+ *               TF32; both non-NULL => 3xTF32, fp32-grade accuracy)
+ * TS kernel (csrc/conv_tc3.cu): the prepared A tiles are written to tensor memory and the MMAs run in TS mode (A from TMEM,
+ * B from shared memory). Takes every shape: the fallback for what the generation-5 kernel below declines. (The round-1
+ * kernels with pre-split operands in HBM -- fpd_conv2d_tc, fpd_conv2d_tc_fused, fpd_conv2d_tc_g -- were removed.) */
 int fpd_conv2d_tc_ts_supported(int Cin, int Cout, int ksize); /* Cout up to 1024, processed in <=128-column slices */
 int fpd_conv2d_tc_ts(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
                      int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
                      const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
                      int ksize, fpd_stream_t stream);
 
-/* Same contract again; the activation tile goes global -> registers -> tensor memory (no shared-memory traffic for the
- * A operand at all; shared memory carries only the weight tiles). */
-int fpd_conv2d_tc_g(const float* x, const float* pre_mean, const float* pre_scale, const float* pre_shift,
-                    int pre_relu, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
-                    const float* relu_mask, float* y, float out_scale, int B, int H, int W, int Cin, int Cout,
-                    int ksize, fpd_stream_t stream);
-
-/* Generation-5 fused convolution (csrc/conv_tc5.cu), same contract as fpd_conv2d_tc_fused. 3x3: the activation tile is
+/* Generation-5 fused convolution (csrc/conv_tc5.cu), same contract as fpd_conv2d_tc_ts. 3x3: the activation tile is
  * fetched with its halo and transformed once per channel block, the nine taps are shifted on-chip copies into tensor
  * memory. f16 = 1 selects 3xFP16 operands (x = hi + lo in fp16, tcgen05.mma kind::f16, fp32 accumulate): w_hi / w_lo
  * are then the __half arrays of fpd_weight_prep_f16; f16 = 0: fp32 containers of fpd_weight_prep (3xTF32).
@@ -147,9 +126,6 @@ int fpd_bn_stats_fused(const float* x, int64_t P, int C, const float* gamma, con
 /* Tensor-core weight gradient: dw_oihw[Cout,Cin,k,k] = scale * sum_pixels dy (x) a(tap-shifted). */
 int fpd_conv2d_wgrad_tc_supported(int Cin, int Cout, int ksize);
 size_t fpd_conv2d_wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize);
-int fpd_conv2d_wgrad_tc(const float* a_hi, const float* a_lo, const float* dy_hi, const float* dy_lo,
-                        float* dw_oihw, float scale, int B, int H, int W, int Cin, int Cout, int ksize,
-                        void* workspace, size_t workspace_bytes, fpd_stream_t stream);
 
 /* Weight gradient with the operand preparation fused in: x and dy are RAW fp32 NHWC tensors; the kernel applies
  * a = relu?((x - pre_mean) * pre_scale + pre_shift) (NULLs = identity), zeroes the 3x3 padding positions and does the

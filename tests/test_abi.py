@@ -24,8 +24,8 @@ def test_library_exports_every_declared_symbol():
     # the ctypes table covers the whole header and nothing else
     assert sorted(N.EXPORTED_SYMBOLS) == declared
     assert N.lib().fpd_version() >= 100
-    assert N.lib().fpd_conv2d_tc_supported(64, 64, 3) == 1
-    assert N.lib().fpd_conv2d_tc_supported(3, 32, 7) == 0
+    assert N.lib().fpd_conv2d_tc_ts_supported(64, 64, 3) == 1
+    assert N.lib().fpd_conv2d_tc_ts_supported(3, 32, 7) == 0
 
 
 def test_missing_library_fails_loudly(tmp_path, monkeypatch):
@@ -49,7 +49,7 @@ def test_every_host_module_imports_on_cpu():
         importlib.import_module("fpd_b200." + name)
     import ast
     for script in ("bench.py", "__graft_entry__.py", "tools/profile_step.py", "tools/profile_kernel.py",
-                   "tools/profile_convs.py", "tools/bench_conv_variants.py", "tools/diag_net.py", "tools/diag_grad.py",
+                   "tools/profile_convs.py", "tools/diag_net.py", "tools/diag_grad.py",
                    "tools/summarize_profiles.py", "tools/diag_conv_h.py", "tools/diag_wgrad.py", "tools/diag_wgrad3.py",
                    "tools/diag_wgrad_shift.py", "tools/timeline_step.py"):
         ast.parse(open(os.path.join(ROOT, script)).read(), script)

@@ -199,7 +199,7 @@ def main():
             h_hi, h_lo = ops.weight_prep_f16(w)
             y = torch.empty(B, H, W, Cout, device="cuda")
             kw = dict(mean=mean, scale=scale, shift=shift, relu=True, out=y, bias=bias, residual=res)
-            t_ts = timed(lambda: ops.conv2d_tc_fused(x, w_hi, w_lo, k, impl="ts", **kw), flush)
+            t_ts = timed(lambda: ops.conv2d_tc_fused(x, w_hi, w_lo, k, **kw), flush)
             t_h = t_f = float("nan")
             if lib.fpd_conv2d_tc_h_supported(Cin, Cout, k, H, W, 0):
                 t_h = timed(lambda: ops.conv2d_tc_h(x, w_hi, w_lo, k, **kw), flush)

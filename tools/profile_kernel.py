@@ -1,8 +1,8 @@
 """Run one libfpd_b200 kernel shape a few times (for `ncu --set full` captures of the hot kernels).
 
-    ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 2 -c 2 \
-        -o gpurun_out/prof_conv_tc python tools/profile_kernel.py conv 32 64 64 128 128 3
-    ncu --set full ... -k regex:wgrad_tc_kernel ... python tools/profile_kernel.py wgrad 32 64 64 64 64 3
+    ncu --set full --clock-control none --import-source on -k regex:conv_tc_h_kernel -s 2 -c 1 \
+        -o gpurun_out/prof_conv_h python tools/profile_kernel.py conv_h_f16 32 64 64 128 128 3
+    ncu --set full ... -k regex:wgrad_tc3_kernel ... python tools/profile_kernel.py wgrad_fused 32 64 64 64 64 3
 """
 import os
 import sys
@@ -22,19 +22,12 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(0)
     x = torch.randn(B, H, W, Cin, device="cuda", generator=g)
     w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * 0.03
-    a_hi, a_lo = ops.affine_act_split(x)
-    if kind == "conv":
-        w_hi, w_lo = ops.weight_prep(w)
-        y = torch.empty(B, H, W, Cout, device="cuda")
-        for _ in range(iters):
-            ops.conv2d_tc(a_hi, a_lo, w_hi, w_lo, k, out=y)
-    elif kind in ("conv_fused", "conv_ts"):
+    if kind == "conv_ts":
         w_hi, w_lo = ops.weight_prep(w)
         y = torch.empty(B, H, W, Cout, device="cuda")
         mean = torch.zeros(Cin, device="cuda"); scale = torch.ones(Cin, device="cuda"); shift = torch.zeros(Cin, device="cuda")
         for _ in range(iters):
-            ops.conv2d_tc_fused(x, w_hi, w_lo, k, mean=mean, scale=scale, shift=shift, relu=True, out=y,
-                                impl="ts" if kind == "conv_ts" else "ss")
+            ops.conv2d_tc_fused(x, w_hi, w_lo, k, mean=mean, scale=scale, shift=shift, relu=True, out=y)
     elif kind in ("conv_h_f16", "conv_h_tf32"):
         prep = ops.weight_prep_f16 if kind == "conv_h_f16" else ops.weight_prep
         w_hi, w_lo = prep(w)
@@ -49,14 +42,6 @@ def main():
         dy = torch.randn(B, H, W, Cout, device="cuda", generator=g)
         for _ in range(iters):
             ops.conv2d_wgrad_tc_fused(x, dy, k, relu=True)
-    elif kind == "wgrad":
-        dy = torch.randn(B, H, W, Cout, device="cuda", generator=g)
-        g_hi, g_lo = ops.affine_act_split(dy)
-        for _ in range(iters):
-            ops.conv2d_wgrad_tc(a_hi, a_lo, g_hi, g_lo, k)
-    elif kind == "split":
-        for _ in range(iters):
-            ops.affine_act_split(x, out_hi=a_hi, out_lo=a_lo)
     else:
         raise SystemExit("unknown kind " + kind)
     torch.cuda.synchronize()
