@@ -587,14 +587,15 @@ def run_b200(args, rank, local_rank, world):
 
 
 def _finish(world, dist):
-    """Leave together and for sure: a last barrier (the other ranks wait for rank 0's side measurements), the process group
-    torn down while every rank is still alive, then a hard exit -- interpreter finalisation with live CUDA graphs / NCCL
-    communicators has been seen to hang a rank for minutes after its work was done (r2 2-GPU run), which a driver that
-    waits for torchrun to exit would count as the job's time."""
+    """Leave together and for sure: a last barrier (the other ranks wait for rank 0's side measurements), then a hard exit.
+    Interpreter finalisation -- and, with NCCL collectives captured inside live CUDA graphs (FPD_BN_SYNC=1), even
+    destroy_process_group() -- has been seen to hang a rank for minutes after its work was done (r2 2-GPU runs), which a
+    driver waiting for torchrun to exit would count as the job's time. The OS reclaims the communicators."""
     if world > 1:
         try:
             dist.barrier()
-            dist.destroy_process_group()
+            import torch
+            torch.cuda.synchronize()
         except Exception:
             pass
         sys.stdout.flush()

@@ -138,10 +138,9 @@ def _sync_worker(rank, world, port, q, use_graph):
     q.close()
     q.join_thread()
     dist.barrier()
-    try:
-        dist.destroy_process_group()
-    finally:
-        os._exit(0)      # CUDA graphs holding NCCL kernels: interpreter finalisation can hang after the work is done
+    torch.cuda.synchronize()
+    # CUDA graphs holding NCCL kernels: destroy_process_group() / interpreter finalisation can hang after the work is done
+    os._exit(0)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
