@@ -68,7 +68,7 @@ CONFIGS = {
         family="hourglass", student=(256, 8), teacher=None, batch=32, H=256, W=256, J=16, lr=0.0,
         flop_per_image=56.189e9, kind="infer", flip=False, roof=dict(cin=128, cout=128, k=3, h=64, w=64)),
 }
-CONV_H_3X3_DRAM_BYTES = 87.09e6   # dram__bytes_read + write, conv_tc_h 3x3 128->128 @64x64 B=32: profiles/r1c_prof_conv_h_3x3.md
+CONV_H_3X3_DRAM_BYTES = 89.88e6   # dram__bytes_read + write, conv_tc_h 3x3 128->128 @64x64 B=32: profiles/r2_prof_conv_h_3x3.md
 
 
 def cfg(f, s, j=16):
@@ -605,7 +605,9 @@ def _finish(world, dist):
 
 # launch-weighted roofline fraction of conv_tc_h_kernel over one whole step (all its launches): conv FLOPs it executes
 # in the step / its summed duration / peak. Filled from profiles/<tag>_launches.csv.gz by tools/summarize_profiles.py.
-LAUNCH_WEIGHTED = {"hg_fpd": 0.062}
+# r2: 2.30 TFLOP of forward + data-gradient convolutions in 24.64 ms summed over its 765 launches (ncu launch list,
+# profiles/r2_launches_summary.md: cold caches, serialised; the warm CUPTI sum of profiles/r2_step_cupti.txt gives 0.064)
+LAUNCH_WEIGHTED = {"hg_fpd": 0.057}
 
 
 def main():
