@@ -17,8 +17,15 @@ struct Best {
   float v;
   int i;
 };
+// numpy semantics: NaN counts as the maximum (np.argmax returns the first NaN, np.amax NaN), otherwise the first
+// occurrence of the largest value
+__device__ __forceinline__ bool beats(float v, float best) { return v > best || (v != v && best == best); }
 __device__ __forceinline__ Best better(Best a, Best b) {
-  // numpy argmax: first occurrence of the maximum
+  const bool an = a.v != a.v, bn = b.v != b.v;
+  if (an || bn) {
+    if (an && bn) return b.i < a.i ? b : a;
+    return bn ? b : a;
+  }
   if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
   return a;
 }
@@ -48,7 +55,7 @@ __global__ void flip_merge_argmax_kernel(const float* __restrict__ hm, const flo
         v = (v + fv) * 0.5f;
       }
       if (avg_nhwc) avg_nhwc[((int64_t)b * hw + p) * J + j] = v;
-      if (v > best.v) { best.v = v; best.i = p; }
+      if (beats(v, best.v)) { best.v = v; best.i = p; }
     }
     sbest[pl * J + j] = best;
   }
@@ -71,7 +78,7 @@ __global__ void argmax_nchw_kernel(const float* __restrict__ hm, int* __restrict
   Best best{-INFINITY, 0x7fffffff};
   for (int i = lane; i < hw; i += 32) {
     const float v = __ldg(p + i);
-    if (v > best.v) { best.v = v; best.i = i; }
+    if (beats(v, best.v)) { best.v = v; best.i = i; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -114,6 +114,24 @@ def _device_accuracy(out_nhwc, target_nchw):
     return avg, cnt, pred
 
 
+def _debug_images(config, input, meta, target, pred, output, prefix):
+    """The reference's debug-image hook (function.py:93-95, 184-186, 289-292; off unless config.DEBUG.DEBUG). It lives in
+    the reference's own utils/vis.py (control plane, cv2 / torchvision): called when that module is importable, i.e. under
+    fpd_b200.dropin.install(); `output` may be an NHWC tensor straight from the engine."""
+    dbg = getattr(config, "DEBUG", None)
+    if dbg is None or not getattr(dbg, "DEBUG", False):
+        return
+    try:
+        from utils.vis import save_debug_images
+    except ImportError:
+        logger.warning("config.DEBUG.DEBUG is set but utils.vis is not importable: no debug images")
+        return
+    if output is not None and output.dim() == 4 and output.shape[1] != target.shape[1]:
+        from fpd_b200 import ops
+        output = ops.nhwc_to_nchw(output.contiguous())
+    save_debug_images(config, input, meta, target, pred * 4, output, prefix)
+
+
 def _log_train(config, writer_dict, epoch, i, n_batches, batch_time, data_time, meters, bsz):
     parts = ['Epoch: [%d][%d/%d]' % (epoch, i, n_batches),
              'Time %.3fs (%.3fs)' % (batch_time.val, batch_time.avg),
@@ -151,7 +169,8 @@ def train(config, train_loader, model, criterion, optimizer, epoch, output_dir, 
             l3, out_nhwc = _fused_step(model, None, input, target, target_weight, 0.0, criterion.use_target_weight)
             optimizer.step()
             losses.update(float(l3[2]), input.size(0))
-            avg_acc, cnt, _ = _device_accuracy(out_nhwc, target)
+            avg_acc, cnt, pred = _device_accuracy(out_nhwc, target)
+            output = out_nhwc
         else:
             outputs = model(input)
             if isinstance(outputs, list):
@@ -166,13 +185,14 @@ def train(config, train_loader, model, criterion, optimizer, epoch, output_dir, 
             loss.backward()
             optimizer.step()
             losses.update(loss.item(), input.size(0))
-            _, avg_acc, cnt, _ = accuracy(output.detach(), target.detach())
+            _, avg_acc, cnt, pred = accuracy(output.detach(), target.detach())
         acc.update(avg_acc, cnt)
         batch_time.update(time.time() - end)
         end = time.time()
         if i % config.PRINT_FREQ == 0:
             _log_train(config, writer_dict, epoch, i, len(train_loader), batch_time, data_time,
                        [('Loss', losses, '%.5f'), ('Accuracy', acc, '%.3f')], input.size(0))
+            _debug_images(config, input, meta, target, pred, output.detach(), '{}_{}'.format(os.path.join(output_dir, 'train'), i))
 
 
 def fpd_train(config, train_loader, model, tmodel, pose_criterion, kd_pose_criterion, optimizer, epoch,
@@ -202,7 +222,8 @@ def fpd_train(config, train_loader, model, tmodel, pose_criterion, kd_pose_crite
                                        pose_criterion.use_target_weight)
             optimizer.step()
             pose_v, kd_v, loss_v = [float(v) for v in l3.cpu()]
-            avg_acc, cnt, _ = _device_accuracy(out_nhwc, target)
+            avg_acc, cnt, pred = _device_accuracy(out_nhwc, target)
+            last_out = out_nhwc
         else:
             outputs = model(input)
             with torch.no_grad():  # the teacher's gradients never reach the student update
@@ -220,7 +241,8 @@ def fpd_train(config, train_loader, model, tmodel, pose_criterion, kd_pose_crite
             loss.backward()
             optimizer.step()
             pose_v, kd_v, loss_v = pose_loss.item(), kd_pose_loss.item(), loss.item()
-            _, avg_acc, cnt, _ = accuracy(outs[-1].detach(), target.detach())
+            _, avg_acc, cnt, pred = accuracy(outs[-1].detach(), target.detach())
+            last_out = outs[-1].detach()
         pose_losses.update(pose_v, input.size(0))
         kd_pose_losses.update(kd_v, input.size(0))
         losses.update(loss_v, input.size(0))
@@ -231,6 +253,7 @@ def fpd_train(config, train_loader, model, tmodel, pose_criterion, kd_pose_crite
             _log_train(config, writer_dict, epoch, i, len(train_loader), batch_time, data_time,
                        [('POSE_Loss', pose_losses, '%.5f'), ('KD_POSE_Loss', kd_pose_losses, '%.5f'),
                         ('Loss', losses, '%.5f'), ('Accuracy', acc, '%.3f')], input.size(0))
+            _debug_images(config, input, meta, target, pred, last_out, '{}_{}'.format(os.path.join(output_dir, 'train'), i))
 
 
 def validate(config, val_loader, val_dataset, model, criterion, output_dir, tb_log_dir, writer_dict=None):
@@ -299,6 +322,7 @@ def validate(config, val_loader, val_dataset, model, criterion, output_dir, tb_l
             if i % config.PRINT_FREQ == 0:
                 logger.info('Test: [%d/%d]\tTime %.3f (%.3f)\tLoss %.4f (%.4f)\tAccuracy %.3f (%.3f)' % (
                     i, len(val_loader), batch_time.val, batch_time.avg, losses.val, losses.avg, acc.val, acc.avg))
+                _debug_images(config, input, meta, target, pred, output, '{}_{}'.format(os.path.join(output_dir, 'val'), i))
         name_values, perf_indicator = val_dataset.evaluate(config, all_preds, output_dir, all_boxes, image_path,
                                                            filenames, imgnums)
         model_name = config.MODEL.NAME
