@@ -80,6 +80,8 @@ class FPDTrainStep:
         self._have_next = False
         self._static_shapes = None
         self._teacher_gen = 0
+        self._stage_x = self._copy_stream = self._stage_ev = self._stage_free = None   # next batch's images, prefetched
+        self._staged_for = None
         self.last_outs = None      # student heat-maps (NHWC, per stack) and the teacher's last stack of the latest step:
         self.last_teacher = None   # kept referenced so the graph's memory pool never recycles them
         self._side = torch.cuda.Stream() if (teacher is not None and self.overlap_teacher) else None
@@ -198,6 +200,8 @@ class FPDTrainStep:
     def step(self, x, target, target_weight, next_x=None):
         """x [B,3,H,W], target [B,J,h,w], target_weight [B,J,1] -- CUDA or pinned-host tensors.
         Returns the device tensor losses[3] = (pose, kd, total); no host synchronisation.
+        `next_x` (optional): the NEXT step's images as a pinned host tensor -- their H2D copy then runs on a copy stream
+        under this step, and the following call must pass that same tensor as `x`.
         With teacher pipelining (`pipeline=True`) pass `next_x`, the NEXT step's images (what a prefetching loader has at
         hand anyway): the teacher runs on them while the student trains on `x`, and the following call must pass that
         same batch as `x`. Without `next_x` the teacher for the following step is run up front (no overlap)."""
@@ -231,9 +235,10 @@ class FPDTrainStep:
                     self.x_next.copy_(next_x, non_blocking=True)
                 self._have_next = next_x is not None
             else:
-                for s, v in zip(self.static, (x, target, tw)):
-                    s.copy_(v, non_blocking=True)
+                self._stage_inputs(x, target, tw)
             self.graph.replay()
+            if not self.pipeline:
+                self._prefetch(next_x)
             losses = self.losses
         else:
             xd, td, wd = (t.cuda(non_blocking=True).float().contiguous() for t in (x, target, tw))
@@ -253,6 +258,38 @@ class FPDTrainStep:
         # Python): drop the student's cached eval-mode operands so a following validation sees the new values
         self.student.engine().invalidate_eval_cache()
         return losses
+
+    # ------------------------------------------------------------------ host batches: H2D of batch i+1 under step i
+    def _stage_inputs(self, x, target, tw):
+        """Bring this step's batch into the graph's static input buffers. If `x` is the pinned host tensor the previous call
+        was given as `next_x`, its images already crossed PCIe on the copy stream while that step computed: only a
+        device-to-device copy (~10 us) is left on the critical path."""
+        main = torch.cuda.current_stream()
+        if self._staged_for is not None and self._staged_for is x:
+            main.wait_event(self._stage_ev)
+            self.static[0].copy_(self._stage_x, non_blocking=True)
+            self._stage_free.record(main)          # the staging buffer may be overwritten once this copy has run
+        else:
+            self.static[0].copy_(x, non_blocking=True)
+        self._staged_for = None
+        self.static[1].copy_(target, non_blocking=True)
+        self.static[2].copy_(tw, non_blocking=True)
+
+    def _prefetch(self, next_x):
+        """Start the H2D copy of the NEXT step's images (a pinned host tensor: what a prefetching DataLoader hands over) on
+        a copy stream, overlapping this step's graph replay."""
+        if next_x is None or next_x.is_cuda or not next_x.is_pinned() or tuple(next_x.shape) != tuple(self.static[0].shape):
+            return
+        if self._stage_x is None or self._stage_x.shape != self.static[0].shape:
+            self._stage_x = torch.empty_like(self.static[0])
+            self._copy_stream = torch.cuda.Stream()
+            self._stage_ev, self._stage_free = torch.cuda.Event(), torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._stage_free)
+            self._stage_x.copy_(next_x, non_blocking=True)
+            self._stage_ev.record(self._copy_stream)
+        self._staged_for = next_x
 
     def invalidate(self):
         """Force a re-capture on the next step (after editing teacher / student tensors in place by hand)."""

@@ -347,3 +347,45 @@ def test_optional_fusions_give_the_same_step():
         assert l2 < 3e-2, (stats, apply_sum, l2)
         assert P.rel_max(got[3]["hg.1.hg.0.3.0.bn2.running_var"], base[3]["hg.1.hg.0.3.0.bn2.running_var"]) < 1e-5
         assert P.rel_max(got[3]["layer3.0.bn1.running_mean"], base[3]["layer3.0.bn1.running_mean"]) < 1e-5
+
+
+def test_prefetched_host_batches_give_the_same_steps():
+    """step(x, ..., next_x=<pinned host tensor>) copies the next batch H2D on a copy stream under the current step; the
+    sequence of losses and the weights must equal plain steps on device-resident batches."""
+    import fpd_b200  # noqa: F401
+    from bench import synthetic_batch
+    from fpd_b200.lib.models import hourglass as H
+    from fpd_b200.train_step import FPDTrainStep
+    from fpd_b200.infer_step import FlipTestInference
+    torch.manual_seed(14)
+    init_s = {k: v.clone() for k, v in H.get_pose_net(_cfg(64, 1), True).state_dict().items()}
+    init_t = {k: v.clone() for k, v in H.get_pose_net(_cfg(64, 1), False).state_dict().items()}
+    host = [tuple(t.pin_memory() for t in synthetic_batch(2, 30 + i, 128, 128)) for i in range(4)]
+
+    def run(prefetch):
+        s = H.get_pose_net(_cfg(64, 1), True)
+        s.load_state_dict(init_s)
+        t = H.get_pose_net(_cfg(64, 1), False)
+        t.load_state_dict(init_t)
+        st = FPDTrainStep(s.cuda(), t.cuda(), lr=1e-3, use_graph=True)
+        out = []
+        for i, (x, tg, tw) in enumerate(host):
+            if prefetch:
+                nxt = host[i + 1][0] if i + 1 < len(host) else None
+                out.append(st.step(x, tg, tw, next_x=nxt).clone())
+            else:
+                out.append(st.step(x.cuda(), tg.cuda(), tw.cuda()).clone())
+        torch.cuda.synchronize()
+        return torch.stack(out).cpu(), st.flat.flat.clone().cpu()
+    l0, w0 = run(False)
+    l1, w1 = run(True)
+    assert torch.equal(l0, l1) and torch.equal(w0, w1)
+    # inference: same indices with and without the prefetch path
+    net = H.get_pose_net(_cfg(64, 1), False).cuda()
+    inf = FlipTestInference(net, [[0, 5], [1, 4]], use_graph=True, want_avg=False)
+    ref = [inf(h[0].cuda())["idx"].clone() for h in host]
+    got = []
+    for i, h in enumerate(host):
+        got.append(inf(h[0], next_x=host[i + 1][0] if i + 1 < len(host) else None)["idx"].clone())
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(ref, got))
