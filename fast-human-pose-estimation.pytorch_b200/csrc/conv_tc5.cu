@@ -45,7 +45,14 @@ constexpr int kMaxCinH = 512;
 constexpr int kParamFloats = kMaxCinH + 64;
 constexpr int kMaxRing = 8;
 constexpr int kTailBytes = 1024 + 3 * kParamFloats * 4;
-constexpr int kEpiBytes = 4 * 32 * 128;   // epilogue staging: one [32 rows x 128 B] tile per epilogue warp
+constexpr int kEpiBytes = 4 * 32 * 128;   // epilogue staging: one [32 rows x 128 B] tile per epilogue warp (3x3 path: 4 warps)
+// 1x1 ("direct") path: the operand transform is light (raw tile -> registers -> TMEM, no tap copies) while the epilogue
+// (TMEM read-out, residual loads, global stores) is what bounds the kernel (r1 stall counters), so the warp budget is
+// re-cut there: 4 transform warps (each thread does both 32-channel halves of its row, waiting for the first half's
+// tcgen05.st before it reuses the registers) and 8 epilogue warps (warps 2-5 take the even 32-column groups of a tile,
+// warps 10-13 the odd ones; a TMEM lane quarter may be read by any warp with the same warp % 4). FPD_CONV_EPI8=0
+// restores the 8 + 4 split of the 3x3 path.
+constexpr int kEpiBytes8 = 8 * 32 * 128;
 
 struct ConvHParams {
   int B, H, W, Cin, Cout;
@@ -75,7 +82,9 @@ struct ConvHParams {
                            // powers of two; puts small-magnitude gradients into the fp16 range, see channel_sum amax)
   double* stat_part;        // kStats: per-CTA column sums of the OUTPUT, [gridDim.x][Cout][2] = {sum (y - pivot), sum (y - pivot)^2}
   const float* stat_pivot;  // nullable [Cout]: per-channel pivot (any value near the channel mean; zero if null)
-  int stat_bytes;           // shared-memory bytes of the per-warp accumulators (4 x Cout x 16), 0 without statistics
+  int stat_bytes;           // shared-memory bytes of the per-warp accumulators (4 or 8 x Cout x 16), 0 without statistics
+  int epi8;                 // 1: direct path with 8 epilogue + 4 transform warps
+  int epi_bytes;            // staging bytes (kEpiBytes or kEpiBytes8)
   long long* prof;   // optional per-CTA stall counters [grid][16] (fpd_conv2d_tc_h_set_profile_buffer); null normally
   int dbg;   // timing ablations only (FPD_CONV_DBG bit mask, tools/diag_conv_h.py): 1 no MMA, 2 no weight TMA, 4 no x TMA,
              // 8 no transform/copy work, 16 no epilogue global traffic, 32 no halo split. Results are garbage when set.
@@ -197,7 +206,7 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   uint8_t* split_base = raw_base + (size_t)p.raw_stages * p.raw_stage_bytes;
   uint8_t* w_base = split_base + p.split_bytes;
   uint8_t* epi_base = w_base + (size_t)p.w_stages * p.w_stage_bytes;
-  uint8_t* tail = epi_base + kEpiBytes;
+  uint8_t* tail = epi_base + p.epi_bytes;
   uint64_t* raw_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* raw_empty = raw_full + kMaxRing;
   uint64_t* w_full = raw_empty + kMaxRing;
@@ -223,17 +232,18 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w_hi);
     if (split) tma_prefetch_desc(&tm_w_lo);
+    const uint32_t n_xf_warps = p.epi8 ? 4u : (uint32_t)(kXf / 32), n_epi_warps = p.epi8 ? 8u : 4u;
     for (int s = 0; s < kMaxRing; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], kXf / 32);
+      mbar_init(&raw_empty[s], n_xf_warps);
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
-      mbar_init(&a_ready[s], kXf / 32);
+      mbar_init(&a_ready[s], n_xf_warps);
       mbar_init(&a_empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], n_epi_warps);
     }
     mbar_fence_init();
   }
@@ -396,21 +406,24 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         o[3] = c_wfull; o[4] = c_aready; o[5] = c_tempty; o[6] = clock64() - c_start;
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 6 || (p.epi8 && warp >= 10)) {
     // ===================== epilogue =====================
     // TMEM -> registers (thread = pixel row) -> per-warp shared-memory staging tile [32 rows x 128 B, chunk-swizzled]
     // -> coalesced global traffic (8 lanes cover one 128-byte row segment: 4 full lines per instruction instead of 32
     // partial ones; the per-thread-row form cost 8k L1 wavefronts per tile and was THE bound of the 1x1 convolutions,
     // tools/diag_conv_h.py --ablate). Residual / bias / mask are applied in the coalesced phase.
-    const int q = warp & 3;
-    const uint32_t stg = smem_u32(epi_base) + (uint32_t)q * 4096u;
+    const int q = warp & 3;                                   // TMEM lane quarter
+    const int e = warp < 6 ? warp - 2 : warp - 10 + 4;        // epilogue warp index 0..7 (4..7 only with epi8)
+    const int cg0 = p.epi8 ? (e >> 2) * 32 : 0;               // first 32-column group of a tile this warp takes
+    const int cgs = p.epi8 ? 64 : 32;                         // ... and its stride
+    const uint32_t stg = smem_u32(epi_base) + (uint32_t)e * 4096u;
     const int sub = lane >> 3, ch = lane & 7;
     const float oscale = p.in_scale ? p.out_scale * __ldg(p.in_scale + 1) : p.out_scale;
     uint32_t tile_iter = 0;
     const bool prof = p.prof != nullptr;
     long long c_tfull = 0;
     const long long c_start = prof ? clock64() : 0;
-    double* my_stat = s_stat + (size_t)q * p.Cout * 2;   // this warp's accumulators
+    double* my_stat = s_stat + (size_t)e * p.Cout * 2;   // this warp's accumulators
     if (kStats) {
       for (int i = lane; i < p.Cout * 2; i += 32) my_stat[i] = 0.0;
       __syncwarp();
@@ -435,7 +448,7 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       // Pull the residual rows towards the L2 one tile ahead (this tile's too, the first time): the loads below then
       // cost an L2 hit instead of an HBM round trip per 32-column group, which was what paced the 1x1 convolutions
       // (epilogue busy 6 us per tile against 3 us of HBM time, tools/diag_conv_h.py --stalls).
-      if (p.residual && !(p.dbg & 16) && ch == 0) {
+      if (p.residual && !(p.dbg & 16) && ch == 0 && e < 4) {
         for (int which = (tile_iter == 0 ? 0 : 1); which < 2; ++which) {
           const int tl = tile + which * (int)gridDim.x;
           if (tl >= p.num_tiles) break;
@@ -454,7 +467,7 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       timed_wait(&tmem_full[acs], acph, prof, c_tfull);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + acs * (uint32_t)p.tmem_cols + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.nt; c0 += 32) {
+      for (int c0 = cg0; c0 < p.nt; c0 += cgs) {
         const int gw = min(32, p.nt - c0);   // 32, or 16 for the last group of a slice that is not a multiple of 32
         const int col = c0 + ch * 4;
         const bool act = ch * 4 < gw;
@@ -543,11 +556,13 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     }
     if (kStats) {
       // merge the four warps in a fixed order and publish this CTA's partial sums
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      const int et = q * 32 + lane;
-      for (int i = et; i < p.Cout * 2; i += 128) {
-        const double v = ((s_stat[i] + s_stat[(size_t)p.Cout * 2 + i]) + s_stat[(size_t)p.Cout * 4 + i]) +
-                         s_stat[(size_t)p.Cout * 6 + i];
+      const int nepi = p.epi8 ? 8 : 4;
+      if (p.epi8) asm volatile("bar.sync 2, 256;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      const int et = e * 32 + lane;
+      for (int i = et; i < p.Cout * 2; i += nepi * 32) {
+        double v = 0.0;
+        for (int w8 = 0; w8 < nepi; ++w8) v += s_stat[(size_t)w8 * p.Cout * 2 + i];   // fixed order
         p.stat_part[(size_t)blockIdx.x * p.Cout * 2 + i] = v;
       }
     }
@@ -582,17 +597,20 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           timed_wait(&a_empty[as_], aph_ ^ 1, prof, c_aempty);
           tc_fence_after_sync();
           const uint32_t rawst = smem_u32(raw_base + (size_t)rs * p.raw_stage_bytes);
+          // epi8: this thread prepares both 32-channel halves of its row, one after the other
+          const int h_lo = p.epi8 ? 0 : half, h_hi = p.epi8 ? 2 : half + 1;
+          for (int hh = h_lo; hh < h_hi; ++hh) {
           uint32_t hi[16], lo[16];
           if (kF16) {
-            // this thread: box `half` (channels 32*half .. +31 of the block), all 8 chunks of its 128-byte row
-            const bool box_ok = inb && (half == 0 || p.Cin - cb * kCB > 32) && !(p.dbg & 8);
-            const uint32_t xrow = rawst + (uint32_t)half * (uint32_t)p.raw_box_bytes + (uint32_t)r * 128u;
+            // box `hh` (channels 32*hh .. +31 of the block), all 8 chunks of this thread's 128-byte row
+            const bool box_ok = inb && (hh == 0 || p.Cin - cb * kCB > 32) && !(p.dbg & 8);
+            const uint32_t xrow = rawst + (uint32_t)hh * (uint32_t)p.raw_box_bytes + (uint32_t)r * 128u;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
               if (box_ok) {
                 v = lds128(xrow + (uint32_t)((i ^ (r & 7)) << 4));
-                v = affine_relu4(v, mean_a, scale_a, shift_a, cb * kCB + half * 32 + i * 4, has_affine, p.pre_relu, in_s);
+                v = affine_relu4(v, mean_a, scale_a, shift_a, cb * kCB + hh * 32 + i * 4, has_affine, p.pre_relu, in_s);
               }
               split_f16x2(v.x, v.y, hi[2 * i], lo[2 * i]);
               split_f16x2(v.z, v.w, hi[2 * i + 1], lo[2 * i + 1]);
@@ -601,7 +619,7 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             const uint32_t xrow = rawst + (uint32_t)r * 128u;
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
-              const int i = half * 4 + ii;
+              const int i = hh * 4 + ii;
               float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
               if (inb && !(p.dbg & 8)) {
                 v = lds128(xrow + (uint32_t)((i ^ (r & 7)) << 4));
@@ -616,11 +634,17 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               lo[ii * 4 + 2] = __float_as_uint(l.z); lo[ii * 4 + 3] = __float_as_uint(l.w);
             }
           }
-          const uint32_t ta = lane_base + (uint32_t)as_ * 64u;
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_col0 + (uint32_t)hh * 16u +
+                              (uint32_t)as_ * 64u;
           if (!(p.dbg & 8)) {
             tmem_st16(ta, hi);
             if (split) tmem_st16(ta + 32u, lo);
+            // tcgen05.st is asynchronous: its source registers must stay untouched until tcgen05.wait::st -- the second
+            // half reuses them, so wait here (without this the A tiles were corrupted whenever the store pipe lagged,
+            // i.e. only inside the concurrent multi-stream step, never kernel by kernel)
+            if (hh + 1 < h_hi) tmem_st_wait();
           }
+          }   // halves
           warp_arrive(&raw_empty[rs], lane);    // every lane's reads of the raw stage have been consumed by the stores above
           if (!(p.dbg & 8)) tmem_st_wait();
           tc_fence_before_sync();
@@ -776,10 +800,13 @@ int align1024(int x) { return (x + 1023) / 1024 * 1024; }
 
 // Fills the geometry / ring sizes; returns false if the shape does not fit.
 bool plan(ConvHParams& p, int B, int H, int W, int Cin, int Cout, int ksize, int f16, int passes, int stats = 0) {
+  static const bool epi8_ok = [] { const char* e = getenv("FPD_CONV_EPI8"); return !(e && e[0] == '0'); }();
+  p.epi8 = (ksize == 1 && epi8_ok) ? 1 : 0;
+  p.epi_bytes = p.epi8 ? kEpiBytes8 : kEpiBytes;
   p.stat_bytes = 0;
   if (stats) {
     if (Cout > 256) return false;
-    p.stat_bytes = 4 * Cout * 16;
+    p.stat_bytes = (p.epi8 ? 8 : 4) * Cout * 16;
   }
   const int cbch = f16 ? 64 : 32;
   if (!(ksize == 1 || ksize == 3)) return false;
@@ -814,7 +841,7 @@ bool plan(ConvHParams& p, int B, int H, int W, int Cin, int Cout, int ksize, int
   if (p.a_stages < 2) return false;
   p.w_tile_bytes = nt * 128;
   p.w_stage_bytes = (passes == 3 ? 2 : 1) * p.w_tile_bytes;
-  const int budget = 227 * 1024 - 1024 - kTailBytes - kEpiBytes - p.stat_bytes;
+  const int budget = 227 * 1024 - 1024 - kTailBytes - p.epi_bytes - p.stat_bytes;
   const int boxes = f16 ? 2 : 1;
   if (ksize == 3) {
     p.halo_w = p.bw + 2; p.halo_h = p.bh + 2;
@@ -895,7 +922,7 @@ int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_sca
   p.prof = g_prof_buf;
   p.in_scale = in_scale;
   const size_t smem_bytes = (size_t)p.raw_stages * p.raw_stage_bytes + p.split_bytes +
-                            (size_t)p.w_stages * p.w_stage_bytes + kEpiBytes + kTailBytes + p.stat_bytes + 1024;
+                            (size_t)p.w_stages * p.w_stage_bytes + p.epi_bytes + kTailBytes + p.stat_bytes + 1024;
   FPD_REQUIRE(smem_bytes <= 227 * 1024, "conv_tc_h: shared memory plan %zu B too large", smem_bytes);
 
   CUtensorMap tm_x, tm_w_hi, tm_w_lo;
