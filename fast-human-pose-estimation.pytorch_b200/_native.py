@@ -69,6 +69,10 @@ _SIGNATURES = {
     "fpd_maxpool2x2_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "fpd_upsample2x_add": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     "fpd_upsample2x_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "fpd_maxpool3x3s2_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "fpd_maxpool3x3s2_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "fpd_depth_space2": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "fpd_deconv_weight_map": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "fpd_subsample2": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "fpd_upsample_zero2": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "fpd_nchw_to_nhwc": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),

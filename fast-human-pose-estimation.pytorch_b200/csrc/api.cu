@@ -281,6 +281,20 @@ int fpd_upsample2x_add(const float* up1, const float* low, float* out, int B, in
 int fpd_upsample2x_bwd(const float* dout, float* dlow, int B, int H, int W, int C, fpd_stream_t stream) {
   return upsample2x_bwd(dout, dlow, B, H, W, C, S(stream));
 }
+int fpd_maxpool3x3s2_fwd(const float* x, float* y, int B, int H, int W, int C, fpd_stream_t stream) {
+  return maxpool3x3s2_fwd(x, y, B, H, W, C, S(stream));
+}
+int fpd_maxpool3x3s2_bwd(const float* x, const float* dy, float* dx, int accumulate, int B, int H, int W, int C,
+                         fpd_stream_t stream) {
+  return maxpool3x3s2_bwd(x, dy, dx, accumulate, B, H, W, C, S(stream));
+}
+int fpd_depth_space2(const float* src, float* dst, int B, int H, int W, int C, int to_depth, fpd_stream_t stream) {
+  return depth_space2(src, dst, B, H, W, C, to_depth, S(stream));
+}
+int fpd_deconv_weight_map(const float* src, float* dst, int Cin, int Cout, int k, int pad, int to_deconv,
+                          fpd_stream_t stream) {
+  return deconv_weight_map(src, dst, Cin, Cout, k, pad, to_deconv, S(stream));
+}
 int fpd_subsample2(const float* x, float* y, int B, int H, int W, int C, fpd_stream_t stream) {
   return subsample2(x, y, B, H, W, C, S(stream));
 }

@@ -41,10 +41,10 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kThreads = 448;
 constexpr int kXf = 256;          // transform threads (warps 6..13)
-constexpr int kMaxCinH = 512;
-constexpr int kParamFloats = kMaxCinH + 64;
+constexpr int kMaxCinH = 2048;              // pose_resnet's layer4 / first deconv
+constexpr int kMinParamFloats = 512 + 64;   // BN parameter arrays in shared memory: sized per launch (ConvHParams::param_floats)
 constexpr int kMaxRing = 8;
-constexpr int kTailBytes = 1024 + 3 * kParamFloats * 4;
+constexpr int tail_bytes_for(int param_floats) { return 1024 + 3 * param_floats * 4; }
 constexpr int kEpiBytes = 4 * 32 * 128;   // epilogue staging: one [32 rows x 128 B] tile per epilogue warp (3x3 path: 4 warps)
 // 1x1 ("direct") path: the operand transform is light (raw tile -> registers -> TMEM, no tap copies) while the epilogue
 // (TMEM read-out, residual loads, global stores) is what bounds the kernel (r1 stall counters), so the warp budget is
@@ -85,6 +85,7 @@ struct ConvHParams {
   int stat_bytes;           // shared-memory bytes of the per-warp accumulators (4 or 8 x Cout x 16), 0 without statistics
   int epi8;                 // 1: direct path with 8 epilogue + 4 transform warps
   int epi_bytes;            // staging bytes (kEpiBytes or kEpiBytes8)
+  int param_floats;         // length of each of the three BN parameter arrays in shared memory (>= Cin rounded up to kCB)
   long long* prof;   // optional per-CTA stall counters [grid][16] (fpd_conv2d_tc_h_set_profile_buffer); null normally
   int dbg;   // timing ablations only (FPD_CONV_DBG bit mask, tools/diag_conv_h.py): 1 no MMA, 2 no weight TMA, 4 no x TMA,
              // 8 no transform/copy work, 16 no epilogue global traffic, 32 no halo split. Results are garbage when set.
@@ -217,9 +218,9 @@ conv_tc_h_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* s_mean = reinterpret_cast<float*>(tail + 1024);
-  float* s_scale = s_mean + kParamFloats;
-  float* s_shift = s_scale + kParamFloats;
-  double* s_stat = reinterpret_cast<double*>(tail + kTailBytes);   // kStats: [4 epilogue warps][Cout][2]
+  float* s_scale = s_mean + p.param_floats;
+  float* s_shift = s_scale + p.param_floats;
+  double* s_stat = reinterpret_cast<double*>(tail + tail_bytes_for(p.param_floats));   // kStats: [4 epilogue warps][Cout][2]
 
   // warp index made provably warp-uniform (shfl broadcast): the single-thread TMA / MMA issue code below then keeps its
   // descriptors in uniform registers. With a threadIdx-derived `if (lane == 0)` around the whole role ptxas wraps every
@@ -811,7 +812,9 @@ bool plan(ConvHParams& p, int B, int H, int W, int Cin, int Cout, int ksize, int
   const int cbch = f16 ? 64 : 32;
   if (!(ksize == 1 || ksize == 3)) return false;
   if (Cin < 4 || Cin > kMaxCinH || Cin % (f16 ? 8 : 4) != 0) return false;
-  if (Cout % 16 != 0 || Cout < 16 || Cout > 1024) return false;
+  if (Cout % 16 != 0 || Cout < 16 || Cout > 2048) return false;
+  p.param_floats = Cin <= 512 ? kMinParamFloats : (Cin + 63) / 64 * 64 + 64;
+  const int kTailBytes = tail_bytes_for(p.param_floats);
   const int nt = conv_tc_ts_slice(Cout);
   if (nt <= 0) return false;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
@@ -922,7 +925,8 @@ int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_sca
   p.prof = g_prof_buf;
   p.in_scale = in_scale;
   const size_t smem_bytes = (size_t)p.raw_stages * p.raw_stage_bytes + p.split_bytes +
-                            (size_t)p.w_stages * p.w_stage_bytes + p.epi_bytes + kTailBytes + p.stat_bytes + 1024;
+                            (size_t)p.w_stages * p.w_stage_bytes + p.epi_bytes + tail_bytes_for(p.param_floats) +
+                            p.stat_bytes + 1024;
   FPD_REQUIRE(smem_bytes <= 227 * 1024, "conv_tc_h: shared memory plan %zu B too large", smem_bytes);
 
   CUtensorMap tm_x, tm_w_hi, tm_w_lo;

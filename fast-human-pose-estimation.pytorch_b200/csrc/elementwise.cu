@@ -727,6 +727,140 @@ __global__ void upsample_zero2_kernel(const float4* __restrict__ dy, float4* __r
   }
 }
 
+// ---- pose_resnet (reference lib/models/pose_resnet.py:107,230-233): nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+// after the stem, NHWC. Padding counts as -inf; the FIRST maximum in window scan order (kh, then kw) wins, like ATen.
+__device__ __forceinline__ bool pool_takes(float v, float m) { return v > m || v != v; }
+
+__global__ void maxpool3x3s2_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int B, int H, int W, int Ho,
+                                        int Wo, int L) {
+  const int64_t n = (int64_t)B * Ho * Wo * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % L);
+    int64_t t = i / L;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int64_t b = t / Ho;
+    const float ninf = __int_as_float(0xff800000);
+    float4 m = make_float4(ninf, ninf, ninf, ninf);
+    for (int kh = 0; kh < 3; ++kh) {
+      const int h = 2 * ho - 1 + kh;
+      if (h < 0 || h >= H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int w = 2 * wo - 1 + kw;
+        if (w < 0 || w >= W) continue;
+        const float4 v = __ldg(x + ((b * H + h) * W + w) * L + cx);
+        if (pool_takes(v.x, m.x)) m.x = v.x;
+        if (pool_takes(v.y, m.y)) m.y = v.y;
+        if (pool_takes(v.z, m.z)) m.z = v.z;
+        if (pool_takes(v.w, m.w)) m.w = v.w;
+      }
+    }
+    y[i] = m;
+  }
+}
+
+// Gather form of the backward (windows overlap, so a scatter would need atomics): every input position looks at the up to
+// four windows that contain it, re-derives each window's winner from x and takes that window's dY where it IS the winner.
+// Deterministic; x is 4 x re-read through L1/L2 (one stem tensor per network).
+__global__ void maxpool3x3s2_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ dy,
+                                        float4* __restrict__ dx, int accumulate, int B, int H, int W, int Ho, int Wo,
+                                        int L) {
+  const int64_t n = (int64_t)B * H * W * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % L);
+    int64_t t = i / L;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int64_t b = t / H;
+    float4 r = accumulate ? dx[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ho0 = h >> 1, ho1 = (h + 1) >> 1, wo0 = w >> 1, wo1 = (w + 1) >> 1;   // 2 ho - 1 <= h <= 2 ho + 1
+    for (int ho = ho0; ho <= ho1; ++ho) {
+      if (ho >= Ho) continue;
+      for (int wo = wo0; wo <= wo1; ++wo) {
+        if (wo >= Wo) continue;
+        const int me = (h - (2 * ho - 1)) * 3 + (w - (2 * wo - 1));   // my position in this window
+        const float ninf = __int_as_float(0xff800000);
+        float4 m = make_float4(ninf, ninf, ninf, ninf);
+        int kx = -1, ky = -1, kz = -1, kw_ = -1;
+        for (int kh = 0; kh < 3; ++kh) {
+          const int hh = 2 * ho - 1 + kh;
+          if (hh < 0 || hh >= H) continue;
+          for (int kw = 0; kw < 3; ++kw) {
+            const int ww = 2 * wo - 1 + kw;
+            if (ww < 0 || ww >= W) continue;
+            const float4 v = __ldg(x + ((b * H + hh) * W + ww) * L + cx);
+            const int k = kh * 3 + kw;
+            if (kx < 0 || pool_takes(v.x, m.x)) { m.x = v.x; kx = k; }
+            if (ky < 0 || pool_takes(v.y, m.y)) { m.y = v.y; ky = k; }
+            if (kz < 0 || pool_takes(v.z, m.z)) { m.z = v.z; kz = k; }
+            if (kw_ < 0 || pool_takes(v.w, m.w)) { m.w = v.w; kw_ = k; }
+          }
+        }
+        const float4 g = __ldg(dy + ((b * Ho + ho) * Wo + wo) * L + cx);
+        if (kx == me) r.x += g.x;
+        if (ky == me) r.y += g.y;
+        if (kz == me) r.z += g.z;
+        if (kw_ == me) r.w += g.w;
+      }
+    }
+    dx[i] = r;
+  }
+}
+
+// ---- ConvTranspose2d(k, stride 2) of pose_resnet's deconv head (pose_resnet.py:176-204) as a stride-1 3x3 convolution to
+// 4 x Cout channels (one group of Cout per output parity (rh, rw)) followed by this depth-to-space shuffle:
+//   out[b, 2a + rh, 2c + rw, co] = y[b, a, c, (2 rh + rw) Cout + co]
+// dir = 0: y [B,H,W,4C] -> out [B,2H,2W,C];  dir = 1: the inverse (= adjoint: a permutation), for the gradient.
+__global__ void depth_space2_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int B, int H, int W, int L,
+                                    int dir) {
+  const int64_t n = (int64_t)B * H * W * 4 * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // i runs over the depth layout [b][a][c][r][co4]
+    const int cx = (int)(i % L);
+    int64_t t = i / L;
+    const int r = (int)(t & 3); t >>= 2;
+    const int c = (int)(t % W); t /= W;
+    const int a = (int)(t % H);
+    const int64_t b = t / H;
+    const int64_t j = ((b * (2 * H) + 2 * a + (r >> 1)) * (2 * W) + 2 * c + (r & 1)) * L + cx;
+    if (dir == 0) dst[j] = __ldg(src + i);
+    else dst[i] = __ldg(src + j);
+  }
+}
+
+// Weights of that equivalent convolution. Transposed convolution: out[oh] += x[ih] Wd[kh] with oh = 2 ih - pad + kh; for
+// oh = 2a + rh and ih = a + dh this is kh = rh + pad - 2 dh, i.e. tap th = dh + 1 of a 3x3 kernel (zero where kh falls
+// outside [0, k)). Wd: [Cin][Cout][k][k] (torch layout), W3: OIHW [4 Cout][Cin][3][3].
+// dir = 0 builds W3 from Wd; dir = 1 gathers dWd from dW3 (every Wd element appears in exactly one place of W3).
+__global__ void deconv_weight_map_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cin, int Cout, int k,
+                                         int pad, int dir) {
+  if (dir == 0) {
+    const int64_t n = (int64_t)4 * Cout * Cin * 9;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const int tw = (int)(i % 3), th = (int)((i / 3) % 3);
+      int64_t t = i / 9;
+      const int ci = (int)(t % Cin); t /= Cin;
+      const int co = (int)(t % Cout);
+      const int r = (int)(t / Cout);
+      const int kh = (r >> 1) + pad - 2 * (th - 1), kw = (r & 1) + pad - 2 * (tw - 1);
+      float v = 0.f;
+      if (kh >= 0 && kh < k && kw >= 0 && kw < k) v = __ldg(src + (((int64_t)ci * Cout + co) * k + kh) * k + kw);
+      dst[i] = v;
+    }
+  } else {
+    const int64_t n = (int64_t)Cin * Cout * k * k;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const int kw = (int)(i % k), kh = (int)((i / k) % k);
+      int64_t t = i / (k * k);
+      const int co = (int)(t % Cout);
+      const int ci = (int)(t / Cout);
+      const int rh = (kh - pad) & 1, rw = (kw - pad) & 1;
+      const int th = (rh + pad - kh) / 2 + 1, tw = (rw + pad - kw) / 2 + 1;   // exact divisions
+      dst[i] = __ldg(src + ((((int64_t)(2 * rh + rw) * Cout + co) * Cin + ci) * 3 + th) * 3 + tw);
+    }
+  }
+}
+
 // NCHW <-> NHWC through a 32x33 shared-memory transpose tile (coalesced on both sides)
 __global__ void transpose_cs_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols, int flip_w) {
   // in: [batch][rows][cols] -> out: [batch][cols][rows]; flip_w > 0 (NCHW -> NHWC only): cols = H * flip_w pixels and the
@@ -1036,6 +1170,46 @@ int upsample_zero2(const float* dy, float* dx, int B, int Ho, int Wo, int C, cud
   FPD_REQUIRE(C % 4 == 0, "upsample_zero2: C=%d must be a multiple of 4", C);
   const int64_t n = (int64_t)B * (2 * Ho) * (2 * Wo) * (C / 4);
   upsample_zero2_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const float4*)dy, (float4*)dx, B, Ho, Wo, C / 4);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int maxpool3x3s2_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0 && H >= 1 && W >= 1, "maxpool3x3s2: bad shape H=%d W=%d C=%d", H, W, C);
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int64_t n = (int64_t)B * Ho * Wo * (C / 4);
+  maxpool3x3s2_fwd_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const float4*)x, (float4*)y, B, H, W, Ho, Wo, C / 4);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int maxpool3x3s2_bwd(const float* x, const float* dy, float* dx, int accumulate, int B, int H, int W, int C,
+                     cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0 && H >= 1 && W >= 1, "maxpool3x3s2_bwd: bad shape H=%d W=%d C=%d", H, W, C);
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int64_t n = (int64_t)B * H * W * (C / 4);
+  maxpool3x3s2_bwd_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const float4*)x, (const float4*)dy, (float4*)dx,
+                                                                accumulate, B, H, W, Ho, Wo, C / 4);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int depth_space2(const float* src, float* dst, int B, int H, int W, int C, int to_depth, cudaStream_t stream) {
+  FPD_REQUIRE(C % 4 == 0 && C > 0, "depth_space2: C=%d must be a positive multiple of 4", C);
+  const int64_t n = (int64_t)B * H * W * 4 * (C / 4);
+  depth_space2_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const float4*)src, (float4*)dst, B, H, W, C / 4,
+                                                            to_depth ? 1 : 0);
+  FPD_LAUNCH_CHECK();
+  return FPD_OK;
+}
+
+int deconv_weight_map(const float* src, float* dst, int Cin, int Cout, int k, int pad, int to_deconv,
+                      cudaStream_t stream) {
+  FPD_REQUIRE((k == 4 && pad == 1) || (k == 3 && pad == 1) || (k == 2 && pad == 0),
+              "deconv_weight_map: (kernel, padding) = (%d, %d) is not one of pose_resnet's (4,1) (3,1) (2,0)", k, pad);
+  FPD_REQUIRE(src && dst && Cin > 0 && Cout > 0, "deconv_weight_map: bad argument");
+  const int64_t n = to_deconv ? (int64_t)Cin * Cout * k * k : (int64_t)4 * Cout * Cin * 9;
+  deconv_weight_map_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src, dst, Cin, Cout, k, pad, to_deconv ? 1 : 0);
   FPD_LAUNCH_CHECK();
   return FPD_OK;
 }

@@ -90,6 +90,13 @@ int maxpool2x2_bwd(const float* x, const float* dy, float* dx, int accumulate, i
 int upsample2x_add(const float* up1, const float* low, float* out, int B, int H, int W, int C,
                    cudaStream_t stream);  // H,W = output size
 int upsample2x_bwd(const float* dout, float* dlow, int B, int H, int W, int C, cudaStream_t stream);
+// pose_resnet stem pool: 3x3, stride 2, padding 1 ([B,H,W,C] -> [B,(H-1)/2+1,(W-1)/2+1,C]); first maximum wins
+int maxpool3x3s2_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream);
+int maxpool3x3s2_bwd(const float* x, const float* dy, float* dx, int accumulate, int B, int H, int W, int C,
+                     cudaStream_t stream);
+// depth [B,H,W,4C] <-> space [B,2H,2W,C] shuffle and the ConvTranspose2d -> 3x3-conv weight map (see elementwise.cu)
+int depth_space2(const float* src, float* dst, int B, int H, int W, int C, int to_depth, cudaStream_t stream);
+int deconv_weight_map(const float* src, float* dst, int Cin, int Cout, int k, int pad, int to_deconv, cudaStream_t stream);
 int subsample2(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream);        // y[ho,wo] = x[2ho,2wo]
 int upsample_zero2(const float* dy, float* dx, int B, int Ho, int Wo, int C, cudaStream_t stream);  // adjoint of subsample2
 int nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream);

@@ -4,10 +4,10 @@ The reference resolves everything by module name after tools/_init_paths.py put 
 (tools/fpd_train.py:27-40: `from core.function import train, fpd_train, validate`, `from core.loss import
 JointsMSELoss`, `eval('models.' + cfg.MODEL.NAME + '.get_pose_net')`, `import dataset` -> `from nms.nms import oks_nms`).
 `install()` replaces exactly the hot-path MODULES in `sys.modules` (and the matching attributes of their parent
-packages) and leaves everything else -- config, dataset, utils.utils, utils.vis, utils.transforms' affine helpers,
-models.pose_resnet -- the reference's own:
+packages) and leaves everything else -- config, dataset, utils.utils, utils.vis, utils.transforms' affine helpers --
+the reference's own:
 
-    models.hourglass, models.pose_hrnet        -> fpd_b200.lib.models.*       (get_pose_net + forward)
+    models.hourglass, .pose_hrnet, .pose_resnet -> fpd_b200.lib.models.*      (get_pose_net + forward)
     core.function                              -> fpd_b200.lib.core.function  (train / fpd_train / validate)
     core.loss, core.inference, core.evaluate   -> fpd_b200.lib.core.*
     nms.nms                                    -> fpd_b200.lib.nms.nms        (gpu_nms, oks_nms, ... full API)
@@ -25,6 +25,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPLACED = {
     "models.hourglass": "fpd_b200.lib.models.hourglass",
     "models.pose_hrnet": "fpd_b200.lib.models.pose_hrnet",
+    "models.pose_resnet": "fpd_b200.lib.models.pose_resnet",
     "core.function": "fpd_b200.lib.core.function",
     "core.loss": "fpd_b200.lib.core.loss",
     "core.inference": "fpd_b200.lib.core.inference",

@@ -74,7 +74,7 @@ STRIDE2_TC = os.environ.get("FPD_STRIDE2_TC", "1") != "0"
 
 
 class ConvRef:
-    __slots__ = ("name", "weight", "bias", "k", "stride", "pad", "cin", "cout", "as_s1")
+    __slots__ = ("name", "weight", "bias", "k", "stride", "pad", "cin", "cout", "as_s1", "pick_first")
 
     def __init__(self, name, mod):
         self.name = name
@@ -88,10 +88,23 @@ class ConvRef:
         # run as a stride-1 convolution + even-position pick (decided per call: needs even H, W)
         self.as_s1 = (STRIDE2_TC and self.stride == 2 and self.k == 3 and self.pad == 1 and self.cin >= 4
                       and mod.kernel_size[1] == 3 and mod.stride[1] == 2)
+        # stride-2 1x1 (pose_resnet's downsample convs, pose_resnet.py:143-148): pick the even positions FIRST, then an
+        # ordinary stride-1 1x1 convolution on a quarter of the pixels
+        self.pick_first = (STRIDE2_TC and self.stride == 2 and self.k == 1 and self.pad == 0 and self.cin >= 4
+                           and mod.kernel_size[1] == 1 and mod.stride[1] == 2)
+
+    @classmethod
+    def derived(cls, name, weight, bias, k, pad):
+        """A stride-1 convolution whose weights are derived from another module's (Engine.deconv)."""
+        c = cls.__new__(cls)
+        c.name, c.weight, c.bias, c.k, c.stride, c.pad = name, weight, bias, k, 1, pad
+        c.cout, c.cin = weight.shape[0], weight.shape[1]
+        c.as_s1 = c.pick_first = False
+        return c
 
     @property
     def s1(self):
-        return self.stride == 1 or self.as_s1
+        return self.stride == 1 or self.as_s1 or self.pick_first
 
     @property
     def im2col_kpad(self):
@@ -100,6 +113,19 @@ class ConvRef:
         if self.cin < 4 and self.k > 1 and K <= 256 and self.cout % 16 == 0 and self.cout <= 256:
             return (K + 31) // 32 * 32
         return 0
+
+    # the TS kernel (csrc/conv_tc3.cu) takes Cin <= 512, Cout <= 1024 at any image size; the generation-5 kernel
+    # (csrc/conv_tc5.cu) up to 2048 channels where its tiling fits (H, W of the call decide)
+    def tc_fwd_at(self, H, W):
+        return self.s1 and self.pad == self.k // 2 and (
+            ops.conv2d_tc_supported(self.cin, self.cout, self.k)
+            or ops.conv2d_tc_h_supported(self.cin, self.cout, self.k, H, W, True))
+
+    def tc_dgrad_at(self, H, W):
+        return self.s1 and self.pad == self.k // 2 and (
+            ops.conv2d_tc_supported(self.cout, self.cin, self.k)
+            or (ops.conv2d_tc_h_supported(self.cout, self.cin, self.k, H, W, True)
+                and ops.conv2d_tc_h_supported(self.cout, self.cin, self.k, H, W, False)))
 
     @property
     def tc_fwd(self):
@@ -132,6 +158,7 @@ class PreparedWeights:
         self.split = passes == 3
         self._fwd = {}
         self._dgrad = {}
+        self.derived = {}      # name -> ConvRef with weights derived from another module's (Engine.deconv)
         # bias-free convolutions get the operand scale of dY from the BatchNorm-backward pass (Engine.force_apply_sum):
         # their 3xFP16 data-gradient weights can then come out of the same launch as the forward ones
         self.scale_without_bias = scale_without_bias
@@ -153,7 +180,7 @@ class PreparedWeights:
             w, k, cin = w2, 1, kpad
         if self.split and ops.CONV_F16 and ops.conv2d_tc_h_supported(cin, c.cout, k, H, W, True):
             if (also_dgrad and not kpad and ops.CONV_F16_DGRAD and ops.FUSED_REDUCE
-                    and (c.bias is not None or self.scale_without_bias) and c.tc_dgrad and ops.conv2d_tc_h_supported(c.cout, c.cin, c.k, H, W, True)):
+                    and (c.bias is not None or self.scale_without_bias) and c.tc_dgrad_at(H, W) and ops.conv2d_tc_h_supported(c.cout, c.cin, c.k, H, W, True)):
                 (hi, lo), (dhi, dlo) = ops.weight_prep_f16_both(w)
                 self._dgrad[c.name] = (dhi, dlo, True)
             else:
@@ -189,11 +216,14 @@ class Engine:
         self.net = net
         self.convs = {}
         self.bns = {}
+        self.deconvs = {}
         for name, m in net.named_modules():
             if isinstance(m, torch.nn.Conv2d):
                 self.convs[name] = ConvRef(name, m)
             elif isinstance(m, torch.nn.BatchNorm2d):
                 self.bns[name] = BNRef(name, m)
+            elif isinstance(m, torch.nn.ConvTranspose2d):
+                self.deconvs[name] = m
         self._eval_cache = None
         self._eval_cache_key = None
         # True: the BatchNorm-backward apply pass always also reduces its output (sum + max |dx|): engines whose convolutions
@@ -330,20 +360,33 @@ class Engine:
         """y = conv(act(bn(x))) + bias (+ residual).  bn_name None -> the conv consumes x raw.
         out_bn: name of a train-mode BatchNorm that will consume y (True: some BatchNorm, name unknown) -- the conv then
         also emits y's per-channel sums from its epilogue (Var.stat_sums), pivoted on that module's running mean."""
-        c = self.convs[conv_name]
+        c = conv_name if isinstance(conv_name, ConvRef) else self.convs[conv_name]
+        if c.pick_first and not getattr(ctx, "_in_s1", False):
+            H_, W_ = x.data.shape[1], x.data.shape[2]
+            if (H_ % 2 == 0 and W_ % 2 == 0 and bn_name is None and residual is None and x.data.shape[-1] % 4 == 0
+                    and c.tc_fwd_at(H_ // 2, W_ // 2)):
+                xs = self.subsample2(ctx, x)
+                ctx._in_s1 = True
+                try:
+                    return self.conv(ctx, xs, c, None, relu, None, need_dx, out_bn=out_bn)
+                finally:
+                    ctx._in_s1 = False
         if c.as_s1 and not getattr(ctx, "_in_s1", False):
             H_, W_ = x.data.shape[1], x.data.shape[2]
-            if (H_ % 2 == 0 and W_ % 2 == 0 and c.cout % 4 == 0 and c.tc_fwd and residual is None
+            if (H_ % 2 == 0 and W_ % 2 == 0 and c.cout % 4 == 0 and c.tc_fwd_at(H_, W_) and residual is None
                     and not (bn_name is None and c.im2col_kpad)):
                 # stride 2 = stride-1 convolution on the tensor cores + even-position pick (recorded as two tape entries:
                 # the pick's backward scatters dY into a zero tensor, the stride-1 conv's backward is the ordinary one)
                 ctx._in_s1 = True
                 try:
-                    full = self.conv(ctx, x, conv_name, bn_name, relu, residual, need_dx, out_bn=None)
+                    full = self.conv(ctx, x, c, bn_name, relu, residual, need_dx, out_bn=None)
                 finally:
                     ctx._in_s1 = False
                 return self.subsample2(ctx, full)
-        s1_ok = c.stride == 1 or getattr(ctx, "_in_s1", False)
+        wrapped = getattr(ctx, "_in_s1", False)        # called by one of the two stride-2 wrappers above
+        s1_ok = c.stride == 1 or wrapped
+        Hx, Wx = x.data.shape[1], x.data.shape[2]
+        tc_fwd = c.tc_fwd_at(Hx, Wx) and s1_ok
         scale = shift = mean = None
         aff = None
         if bn_name is not None:
@@ -380,7 +423,7 @@ class Engine:
                                                          pad=c.pad), owned=True)
                 ctx.tape.append(bwd_stem)
             return out
-        if c.tc_fwd and s1_ok:
+        if tc_fwd:
             w_hi, w_lo, use_h = ctx.weights.fwd(c, x.data.shape[1], x.data.shape[2],
                                                 also_dgrad=ctx.tape is not None and need_dx)
             stat_sums = None
@@ -404,12 +447,12 @@ class Engine:
             a = ops.affine_act(x.data, scale, shift, relu, mean=mean) if bn_name is not None else x.data
             y = ops.conv2d_simt_fwd(a, c.weight.detach(), bias=bias, residual=res, stride=c.stride, pad=c.pad)
         out = Var(y)
-        if c.tc_fwd and s1_ok:
+        if tc_fwd:
             out.stat_sums = stat_sums
         tc_wgrad = c.tc_wgrad and s1_ok
-        tc_dgrad = c.tc_dgrad and s1_ok
-        in_s1 = c.as_s1 and s1_ok            # stride-2 conv running as stride 1 + pick: dY arrives zero-upsampled
-        stride_eff = 1 if in_s1 else c.stride
+        tc_dgrad = c.tc_dgrad_at(Hx, Wx) and s1_ok
+        in_s1 = c.as_s1 and wrapped          # stride-2 3x3 running as stride 1 + pick: dY arrives zero-upsampled
+        stride_eff = 1 if wrapped else c.stride   # (pick-first 1x1: x is already the picked tensor, a true stride-1 conv)
         wgrad_chunks = None                  # too wide for one tensor-core wgrad launch: one launch per channel chunk
         if (ctx.tape is not None and not tc_wgrad and s1_ok and c.pad == c.k // 2
                 and (bn_name is not None or not c.im2col_kpad)):
@@ -455,7 +498,8 @@ class Engine:
                     # CUDA-core fallback; for a stride-2 conv in stride-1 mode go back to the compact dY (the even
                     # positions of the zero-upsampled one) and the true stride: a quarter of the work
                     dy_w = ops.subsample2(dy) if in_s1 else dy
-                    ctx.pgrads[c.weight] = ops.conv2d_simt_wgrad(a_full, dy_w, c.k, stride=c.stride, pad=c.pad)
+                    ctx.pgrads[c.weight] = ops.conv2d_simt_wgrad(a_full, dy_w, c.k, stride=c.stride if (in_s1 or not wrapped) else 1,
+                                                                 pad=c.pad)
                 if not need_dx:
                     return
                 # ---- data gradient w.r.t. the conv input a = act(bn(x))
@@ -487,6 +531,61 @@ class Engine:
                 x.add_grad(ops.upsample_zero2(out.grad), owned=True)
                 if fresh and gs is not None:
                     x.grad_sum = gs       # zeros add nothing: the per-channel sums and the maximum carry over unchanged
+            ctx.tape.append(bwd)
+        return out
+
+    def deconv(self, ctx, x, name, bn_name=None, relu=False):
+        """y = ConvTranspose2d_{k, stride 2}(act(bn(x))) (pose_resnet.py:176-204) = depth_to_space(conv3x3_{4 Cout}(...)):
+        the four output parities of a stride-2 transposed convolution are four 2x2-tap convolutions of the input, written
+        here as ONE 3x3 convolution with structurally zero taps (2.25 x the MACs, but on the tensor-core path with the
+        BN + ReLU + split operand pass, the 3xFP16 data gradient and the tensor-core weight gradient that come with it)."""
+        m = self.deconvs[name]
+        k, pad = m.kernel_size[0], m.padding[0]
+        if not (m.stride == (2, 2) and m.kernel_size[1] == k and (k, pad, m.output_padding[0]) in ((4, 1, 0), (3, 1, 1), (2, 0, 0))
+                and m.groups == 1 and m.dilation == (1, 1)):
+            raise NotImplementedError("deconv %s: only pose_resnet's stride-2 (kernel, padding, output_padding) = "
+                                      "(4,1,0) (3,1,1) (2,0,0) are implemented" % name)
+        cached = ctx.weights.derived.get(name)
+        if cached is None:
+            w3 = ops.deconv_weight_to_conv3(m.weight.detach(), pad)
+            b3 = m.bias.detach().repeat(4) if m.bias is not None else None
+            cached = ConvRef.derived(name, w3, b3, 3, 1)
+            ctx.weights.derived[name] = cached
+        c = cached
+        if ctx.tape is not None:
+            def bwd_map():      # recorded BEFORE the convolution: runs after its backward
+                dw3 = ctx.pgrads.pop(c.weight, None)
+                if dw3 is None:
+                    return
+                if ctx.wgrad_stream is not None:
+                    torch.cuda.current_stream().wait_stream(ctx.wgrad_stream)
+                ctx.pgrads[m.weight] = ops.conv3_grad_to_deconv(dw3, k, pad)
+                if c.bias is not None:
+                    ctx.pgrads[m.bias] = ctx.pgrads.pop(c.bias).view(4, -1).sum(0)
+            ctx.tape.append(bwd_map)
+        y = self.conv(ctx, x, c, bn_name, relu)
+        out = Var(ops.depth_to_space2(y.data))
+        if ctx.tape is not None:
+            def bwd():
+                if out.grad is None:
+                    return
+                gs = out.grad_sum
+                y.add_grad(ops.space_to_depth2(out.grad), owned=True)
+                if gs is not None and c.bias is None:
+                    y.grad_sum = (None, gs[1])     # a permutation: the maximum, hence the operand scale, carries over
+            ctx.tape.append(bwd)
+        return out
+
+    def maxpool3(self, ctx, x):
+        """nn.MaxPool2d(3, 2, 1) of the pose_resnet stem."""
+        out = Var(ops.maxpool3x3s2(x.data))
+        if ctx.tape is not None:
+            def bwd():
+                if out.grad is None:
+                    return
+                tgt = x.accum_target()
+                dx = ops.maxpool3x3s2_bwd(x.data, out.grad, accumulate_into=tgt)
+                x.set_or_merge(dx, tgt is not None)
             ctx.tape.append(bwd)
         return out
 

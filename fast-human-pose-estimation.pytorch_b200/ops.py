@@ -283,33 +283,37 @@ def conv2d_wgrad_tc_fused(x, dy, ksize, mean=None, scale=None, shift=None, relu=
 
 
 def wgrad_channel_chunks(cin, cout, k):
-    """Split of the input channels into widths the tensor-core weight-gradient kernels take (M = Cin in {128, 64, 32}), for
-    convolutions that are too wide for one launch (HRNet: 256-channel 3x3). None if some remainder cannot be covered."""
-    if conv2d_wgrad_tc_supported(cin, cout, k):
-        return [cin]
-    chunks, rest = [], cin
-    for w in (128, 64, 32):
-        while rest >= w and conv2d_wgrad_tc_supported(w, cout, k):
-            chunks.append(w)
-            rest -= w
-    return chunks if rest == 0 and chunks else None
+    """(input-channel chunk, output-channel chunk) widths the tensor-core weight-gradient kernels take, for convolutions
+    that are too wide for one launch (HRNet's 256-channel 3x3, pose_resnet's 512..2048-channel layers); the largest
+    supported pair of divisors. None if there is none."""
+    for co in (cout, 256, 128, 64, 32):
+        if co > cout or cout % co:
+            continue
+        for ci in (cin, 256, 128, 64, 32):
+            if ci > cin or cin % ci:
+                continue
+            if conv2d_wgrad_tc_supported(ci, co, k):
+                return ci, co
+    return None
 
 
 def conv2d_wgrad_tc_chunked(x, dy, ksize, chunks, mean=None, scale=None, shift=None, relu=False, passes=3):
-    """dW of a wide convolution as one tensor-core weight-gradient launch per input-channel chunk: the chunk of x is made
-    contiguous (a strided copy -- these tensors are the low-resolution HRNet branches), its BN parameters are slices."""
+    """dW of a wide convolution as one tensor-core weight-gradient launch per (input-channel, output-channel) chunk: the
+    chunks of x / dY are made contiguous (strided copies -- these are the low-resolution, many-channel tensors), the BN
+    parameters are slices."""
     Cin = x.shape[-1]
     Cout = dy.shape[-1]
+    ci, co = chunks
     dw = torch.empty((Cout, Cin, ksize, ksize), dtype=torch.float32, device=x.device)
-    c0 = 0
-    for cw in chunks:
-        xs = x[..., c0:c0 + cw].contiguous()
-        sl = slice(c0, c0 + cw)
-        dws = conv2d_wgrad_tc_fused(xs, dy, ksize, mean=None if mean is None else mean[sl],
-                                    scale=None if scale is None else scale[sl],
-                                    shift=None if shift is None else shift[sl], relu=relu, passes=passes)
-        dw[:, sl] = dws
-        c0 += cw
+    dys = [dy if co == Cout else dy[..., o0:o0 + co].contiguous() for o0 in range(0, Cout, co)]
+    for c0 in range(0, Cin, ci):
+        sl = slice(c0, c0 + ci)
+        xs = x if ci == Cin else x[..., sl].contiguous()
+        for j, o0 in enumerate(range(0, Cout, co)):
+            dws = conv2d_wgrad_tc_fused(xs, dys[j], ksize, mean=None if mean is None else mean[sl],
+                                        scale=None if scale is None else scale[sl],
+                                        shift=None if shift is None else shift[sl], relu=relu, passes=passes)
+            dw[o0:o0 + co, sl] = dws
     return dw
 
 
@@ -454,6 +458,56 @@ def upsample2x_bwd(dout, out=None):
     d = out if out is not None else torch.empty((B, H // 2, W // 2, C), dtype=torch.float32, device=dout.device)
     N.check(N.lib().fpd_upsample2x_bwd(_p(dout), _p(d), B, H, W, C, _stream()), "upsample2x_bwd")
     return d
+
+
+def maxpool3x3s2(x):
+    """nn.MaxPool2d(3, stride=2, padding=1) on NHWC (pose_resnet stem, reference pose_resnet.py:107)."""
+    B, H, W, C = x.shape
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=x.dtype, device=x.device)
+    N.check(N.lib().fpd_maxpool3x3s2_fwd(_p(x), _p(y), B, H, W, C, _stream()), "maxpool3x3s2_fwd")
+    return y
+
+
+def maxpool3x3s2_bwd(x, dy, accumulate_into=None):
+    B, H, W, C = x.shape
+    dx = accumulate_into if accumulate_into is not None else torch.empty_like(x)
+    N.check(N.lib().fpd_maxpool3x3s2_bwd(_p(x), _p(dy), _p(dx), int(accumulate_into is not None), B, H, W, C, _stream()),
+            "maxpool3x3s2_bwd")
+    return dx
+
+
+def depth_to_space2(y):
+    """[B,H,W,4C] -> [B,2H,2W,C]: out[b,2a+rh,2c+rw,co] = y[b,a,c,(2rh+rw)C+co] (tail of the deconv-as-3x3-conv)."""
+    B, H, W, C4 = y.shape
+    C = C4 // 4
+    out = torch.empty((B, 2 * H, 2 * W, C), dtype=y.dtype, device=y.device)
+    N.check(N.lib().fpd_depth_space2(_p(y), _p(out), B, H, W, C, 0, _stream()), "depth_to_space2")
+    return out
+
+
+def space_to_depth2(g):
+    """Inverse (= adjoint) of depth_to_space2: [B,2H,2W,C] -> [B,H,W,4C]."""
+    B, H2, W2, C = g.shape
+    out = torch.empty((B, H2 // 2, W2 // 2, 4 * C), dtype=g.dtype, device=g.device)
+    N.check(N.lib().fpd_depth_space2(_p(g), _p(out), B, H2 // 2, W2 // 2, C, 1, _stream()), "space_to_depth2")
+    return out
+
+
+def deconv_weight_to_conv3(wd, pad):
+    """ConvTranspose2d weight [Cin,Cout,k,k] (stride 2) -> OIHW [4*Cout,Cin,3,3] of the equivalent stride-1 convolution."""
+    Cin, Cout, k, _ = wd.shape
+    w3 = torch.empty((4 * Cout, Cin, 3, 3), dtype=torch.float32, device=wd.device)
+    N.check(N.lib().fpd_deconv_weight_map(_p(wd), _p(w3), Cin, Cout, k, int(pad), 0, _stream()), "deconv_weight_map")
+    return w3
+
+
+def conv3_grad_to_deconv(dw3, k, pad):
+    """Gradient of the ConvTranspose2d weight out of the equivalent convolution's [4*Cout,Cin,3,3] weight gradient."""
+    Cout, Cin = dw3.shape[0] // 4, dw3.shape[1]
+    dwd = torch.empty((Cin, Cout, k, k), dtype=torch.float32, device=dw3.device)
+    N.check(N.lib().fpd_deconv_weight_map(_p(dw3), _p(dwd), Cin, Cout, int(k), int(pad), 1, _stream()),
+            "deconv_weight_map")
+    return dwd
 
 
 def subsample2(x, out=None):

@@ -216,6 +216,22 @@ int fpd_maxpool2x2_bwd(const float* x, const float* dy, float* dx, int accumulat
 int fpd_upsample2x_add(const float* up1, const float* low, float* out, int B, int H, int W, int C,
                        fpd_stream_t stream); /* H,W = output size */
 int fpd_upsample2x_bwd(const float* dout, float* dlow, int B, int H, int W, int C, fpd_stream_t stream);
+/* pose_resnet (lib/models/pose_resnet.py). Stem pool nn.MaxPool2d(3, 2, 1) (:107,233), NHWC: x [B,H,W,C] ->
+ * y [B,(H-1)/2+1,(W-1)/2+1,C], padding = -inf, first maximum in window scan order wins (ATen); the backward is a
+ * deterministic gather (accumulate != 0: dx += ...). C % 4 == 0. */
+int fpd_maxpool3x3s2_fwd(const float* x, float* y, int B, int H, int W, int C, fpd_stream_t stream);
+int fpd_maxpool3x3s2_bwd(const float* x, const float* dy, float* dx, int accumulate, int B, int H, int W, int C,
+                         fpd_stream_t stream);
+/* The deconv head nn.ConvTranspose2d(Cin, Cout, k, stride=2, padding=pad) (:176-204; (k,pad) in (4,1) (3,1) (2,0)) runs as
+ * a stride-1 3x3 convolution to 4*Cout channels on the tensor-core kernels + a depth-to-space shuffle:
+ * fpd_deconv_weight_map(to_deconv=0) builds the OIHW [4*Cout,Cin,3,3] weights from the module's [Cin,Cout,k,k] ones,
+ * (to_deconv=1) gathers the module's weight gradient back out of the convolution's; fpd_depth_space2(to_depth=0) maps
+ * src [B,H,W,4C] -> dst [B,2H,2W,C], dst[b,2a+rh,2c+rw,co] = src[b,a,c,(2rh+rw)C+co]; (to_depth=1) is the inverse, src
+ * [B,2H,2W,C] -> dst [B,H,W,4C] (B, H, W, C always name the DEPTH side's [B,H,W,4C]). */
+int fpd_depth_space2(const float* src, float* dst, int B, int H, int W, int C, int to_depth, fpd_stream_t stream);
+int fpd_deconv_weight_map(const float* src, float* dst, int Cin, int Cout, int k, int pad, int to_deconv,
+                          fpd_stream_t stream);
+
 /* Stride-2 3x3 convolutions (HRNet stem / transition / fuse down paths, lib/models/pose_hrnet.py:213-239,281-284,355-370)
  * on the stride-1 tensor-core kernels: y = subsample2(conv_s1(x)) picks the even positions (x: [B,H,W,C] -> y:
  * [B,H/2,W/2,C]); upsample_zero2 is its adjoint (dY scattered to the even positions of a zero [B,2Ho,2Wo,C] tensor), which

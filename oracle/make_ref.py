@@ -20,6 +20,7 @@ DST = os.path.join(HERE, "_ref")
 FILES = [
     "lib/models/hourglass.py",      # Bottleneck / Hourglass / HourglassNet / get_pose_net
     "lib/models/pose_hrnet.py",     # HRNet (a5-a7)
+    "lib/models/pose_resnet.py",    # ResNet + deconv head (f4)
     "lib/core/loss.py",             # JointsMSELoss (a8)
     "lib/core/inference.py",        # get_max_preds / get_final_preds (a11, f1)
     "lib/core/evaluate.py",         # accuracy (f1)

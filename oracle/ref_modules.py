@@ -40,6 +40,18 @@ def pose_hrnet():
     return _cache["hr"]
 
 
+def pose_resnet():
+    if "rn" not in _cache:
+        _cache["rn"] = _load("fpd_ref_pose_resnet", "lib/models/pose_resnet.py")
+    return _cache["rn"]
+
+
+def resnet_cfg(num_layers, j=16, deconv=(256, 256, 256), kernels=(4, 4, 4), final_kernel=1, deconv_bias=False):
+    return NS(MODEL=NS(NUM_JOINTS=j, INIT_WEIGHTS=False, PRETRAINED='', EXTRA=NS(
+        NUM_LAYERS=num_layers, DECONV_WITH_BIAS=deconv_bias, NUM_DECONV_LAYERS=len(deconv),
+        NUM_DECONV_FILTERS=list(deconv), NUM_DECONV_KERNELS=list(kernels), FINAL_CONV_KERNEL=final_kernel)))
+
+
 def loss():
     if "loss" not in _cache:
         _cache["loss"] = _load("fpd_ref_loss", "lib/core/loss.py")

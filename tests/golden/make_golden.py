@@ -158,9 +158,71 @@ def main_decode2():
     print("decode2.npz", os.path.getsize(os.path.join(OUT, "decode2.npz")))
 
 
+RESNET_CASES = {   # tag: (NUM_LAYERS, joints, deconv filters, deconv kernels, FINAL_CONV_KERNEL, DECONV_WITH_BIAS)
+    "r18": (18, 17, (64, 32, 32), (4, 3, 2), 3, True),       # BasicBlock; every head geometry of pose_resnet.py:159-174
+    "r50": (50, 16, (128, 64, 64), (4, 4, 4), 1, False),     # Bottleneck; the shipped configs' geometry
+}
+
+
+def resnet_cfg(layers, j, filters, kernels, fk, bias):
+    return NS(MODEL=NS(NUM_JOINTS=j, INIT_WEIGHTS=False, PRETRAINED='', EXTRA=NS(
+        NUM_LAYERS=layers, DECONV_WITH_BIAS=bias, NUM_DECONV_LAYERS=len(filters), NUM_DECONV_FILTERS=list(filters),
+        NUM_DECONV_KERNELS=list(kernels), FINAL_CONV_KERNEL=fk)))
+
+
+def grad_digest(g):
+    """Whole tensor when small, else its first 512 entries + L2 norm (ResNet gradients are too large to commit)."""
+    g = g.detach().reshape(-1)
+    return (g.numpy() if g.numel() <= 2048 else g[:512].numpy()), np.float64(g.double().norm().item())
+
+
+def main_resnet():
+    """Section 7: the reference's lib/models/pose_resnet.py (ResNet-18 and -50 bodies, all three deconv geometries) on
+    oracle.resnet_oracle.synthetic_state() weights -- regenerated from the seed by the tests, the networks are too large to
+    commit -- 64x64 inputs, train-mode forward + JointsMSELoss + backward, and the eval-mode forward."""
+    sys.path.insert(0, os.path.join(OUT, "..", ".."))
+    from oracle.resnet_oracle import synthetic_state
+    torch.set_num_threads(4)
+    R = load("ref_pose_resnet", "lib/models/pose_resnet.py")
+    L = load("ref_loss", "lib/core/loss.py")
+    crit = L.JointsMSELoss(use_target_weight=True)
+    save = {}
+    for tag, (layers, J, filters, kernels, fk, bias) in RESNET_CASES.items():
+        net = R.get_pose_net(resnet_cfg(layers, J, filters, kernels, fk, bias), is_train=False)
+        sd0 = synthetic_state({k: v.shape for k, v in net.state_dict().items()}, seed=7)
+        net.load_state_dict(sd0, strict=True)
+        rng = np.random.RandomState(11)
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn(2, 3, 64, 64, generator=g)
+        target = torch.from_numpy(gaussian_targets(rng, 2, J, 16, 16))
+        tw = torch.from_numpy((rng.rand(2, J, 1) > 0.2).astype(np.float32))
+        net.train()
+        out = net(x)
+        loss = crit(out, target, tw)
+        loss.backward()
+        save[tag + "/x"], save[tag + "/target"], save[tag + "/target_weight"] = x.numpy(), target.numpy(), tw.numpy()
+        save[tag + "/out_train"] = out.detach().numpy()
+        save[tag + "/loss"] = np.float64(loss.item())
+        for k, p_ in net.named_parameters():
+            d, n = grad_digest(p_.grad)
+            save["%s/grad/%s" % (tag, k)] = d
+            save["%s/gnorm/%s" % (tag, k)] = n
+        save[tag + "/bn1.running_mean"] = net.bn1.running_mean.numpy().copy()
+        save[tag + "/bn1.running_var"] = net.bn1.running_var.numpy().copy()
+        net.load_state_dict(sd0)
+        net.eval()
+        with torch.no_grad():
+            save[tag + "/out_eval"] = net(x).numpy()
+        save[tag + "/keys"] = np.array(list(net.state_dict().keys()))
+    np.savez_compressed(os.path.join(OUT, "resnet_small.npz"), **save)
+    print("resnet_small.npz", os.path.getsize(os.path.join(OUT, "resnet_small.npz")))
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "decode2":
         return main_decode2()
+    if len(sys.argv) > 1 and sys.argv[1] == "resnet":
+        return main_resnet()
     torch.set_num_threads(4)
     hg = load("ref_hourglass", "lib/models/hourglass.py")
     loss_mod = load("ref_loss", "lib/core/loss.py")

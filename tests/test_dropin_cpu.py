@@ -56,9 +56,8 @@ SCRIPT = textwrap.dedent('''
     ours = lambda o: o.__module__.startswith("fpd_b200.")
     assert ours(JointsMSELoss) and ours(train) and ours(fpd_train) and ours(validate)
     assert not ours(get_optimizer)
-    for name in ("hourglass", "pose_hrnet"):
+    for name in ("hourglass", "pose_hrnet", "pose_resnet"):
         assert ours(eval("models." + name + ".get_pose_net")), name
-    assert not ours(eval("models.pose_resnet.get_pose_net"))           # not on the hot path: the reference's own
     # modules the reference's dataset / vis code needs from the packages we touch
     from utils.transforms import get_affine_transform, affine_transform, fliplr_joints, transform_preds, flip_back
     assert not ours(get_affine_transform) and ours(flip_back)

@@ -193,6 +193,110 @@ def test_hrnet_dropin_state_dict_matches_reference_keys():
         net(torch.zeros(1, 3, 64, 64))
 
 
+# ---------------------------------------------------------------------------------------------- pose_resnet
+RESNET_CASES = {"r18": (18, 17, (64, 32, 32), (4, 3, 2), 3, True), "r50": (50, 16, (128, 64, 64), (4, 4, 4), 1, False)}
+
+
+def _resnet_cfg(tag):
+    layers, J, filters, kernels, fk, bias = RESNET_CASES[tag]
+    NS = types.SimpleNamespace
+    return NS(MODEL=NS(NUM_JOINTS=J, INIT_WEIGHTS=False, PRETRAINED='', EXTRA=NS(
+        NUM_LAYERS=layers, DECONV_WITH_BIAS=bias, NUM_DECONV_LAYERS=len(filters), NUM_DECONV_FILTERS=list(filters),
+        NUM_DECONV_KERNELS=list(kernels), FINAL_CONV_KERNEL=fk)))
+
+
+def _resnet_state(tag):
+    """The golden run's weights, regenerated from the seed over the drop-in's own state_dict layout."""
+    import fpd_b200  # noqa: F401
+    from fpd_b200.lib.models import pose_resnet as R
+    from oracle.resnet_oracle import synthetic_state
+    net = R.get_pose_net(_resnet_cfg(tag), is_train=False)
+    return net, synthetic_state({k: v.shape for k, v in net.state_dict().items()}, seed=7)
+
+
+@pytest.mark.parametrize("tag", ["r18", "r50"])
+def test_resnet_oracle_matches_reference_golden(tag):
+    from oracle import resnet_oracle as RO
+    torch.set_num_threads(4)
+    g = {k[len(tag) + 1:]: v for k, v in _load("resnet_small.npz").items() if k.startswith(tag + "/")}
+    net, sd = _resnet_state(tag)
+    assert list(net.state_dict().keys()) == [str(k) for k in g["keys"]]       # the reference's keys, in its order
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.dtype == torch.float32 and "running" not in k}
+    sd = dict(sd)
+    sd.update(params)
+    x = torch.from_numpy(g["x"])
+    out = RO.resnet(sd, x, training=True)
+    assert _rel(out.detach(), g["out_train"]) < 2e-5
+    loss = O.joints_mse(out, torch.from_numpy(g["target"]), torch.from_numpy(g["target_weight"]))
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    assert _rel(sd["bn1.running_mean"], g["bn1.running_mean"]) < 1e-5       # train-mode side effect, momentum 0.1
+    assert _rel(sd["bn1.running_var"], g["bn1.running_var"]) < 1e-5
+    worst = 0.0
+    for k, p in params.items():
+        gd = p.grad.reshape(-1)
+        ref = torch.from_numpy(g["grad/" + k])
+        n = float(g["gnorm/" + k])
+        # digest: leading entries (whole tensor when small) relative to the tensor's RMS, plus the L2 norm
+        rms = max(n / gd.numel() ** 0.5, 1e-30)
+        worst = max(worst, ((gd[:ref.numel()] - ref).abs().max() / rms).item())
+        assert abs(gd.double().norm().item() - n) <= 2e-3 * n + 1e-12, k
+    assert worst < 5e-3, worst
+    _, sd_eval = _resnet_state(tag)
+    with torch.no_grad():
+        assert _rel(RO.resnet(sd_eval, x, training=False), g["out_eval"]) < 2e-5
+
+
+def test_resnet_dropin_matches_reference_layout_and_refuses_cpu():
+    net, sd = _resnet_state("r50")
+    net.load_state_dict(sd, strict=True)
+    assert type(net.deconv_layers[0]).__name__ == "ConvTranspose2d" and net.deconv_layers[0].bias is None
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        net(torch.zeros(1, 3, 64, 64))
+    if os.path.isdir(REF):        # live reference: every depth of resnet_spec has the same keys / shapes
+        spec = importlib.util.spec_from_file_location("ref_pose_resnet_t", os.path.join(REF, "lib/models/pose_resnet.py"))
+        R = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(R)
+        from fpd_b200.lib.models import pose_resnet as M
+        assert {k: v[1] for k, v in M.resnet_spec.items()} == {k: v[1] for k, v in R.resnet_spec.items()}
+        for tag in ("r18", "r50"):
+            a = R.get_pose_net(_resnet_cfg(tag), is_train=False).state_dict()
+            b = M.get_pose_net(_resnet_cfg(tag), is_train=False).state_dict()
+            assert list(a.keys()) == list(b.keys()) and all(a[k].shape == b[k].shape for k in a)
+
+
+@pytest.mark.parametrize("k,pad,outpad", [(4, 1, 0), (3, 1, 1), (2, 0, 0)])
+def test_transposed_conv_as_3x3_conv_plus_depth_to_space(k, pad, outpad):
+    """The identity Engine.deconv / csrc/elementwise.cu deconv_weight_map_kernel rest on, in plain torch:
+    ConvTranspose2d(k, stride 2, pad) == depth_to_space(conv3x3(x, W3)), W3[(rh,rw,co), ci, th, tw] =
+    Wd[ci, co, rh + pad - 2 (th - 1), rw + pad - 2 (tw - 1)] (zero outside the kernel); and the gradient map back."""
+    g = torch.Generator().manual_seed(k)
+    Cin, Cout, H, W = 5, 3, 6, 4
+    x = torch.randn(2, Cin, H, W, generator=g, dtype=torch.float64)
+    wd = torch.randn(Cin, Cout, k, k, generator=g, dtype=torch.float64)
+    ref = torch.nn.functional.conv_transpose2d(x, wd, stride=2, padding=pad, output_padding=outpad)
+    w3 = torch.zeros(2, 2, Cout, Cin, 3, 3, dtype=torch.float64)
+    where = {}
+    for rh in range(2):
+        for rw in range(2):
+            for th in range(3):
+                for tw in range(3):
+                    kh, kw = rh + pad - 2 * (th - 1), rw + pad - 2 * (tw - 1)
+                    if 0 <= kh < k and 0 <= kw < k:
+                        w3[rh, rw, :, :, th, tw] = wd[:, :, kh, kw].t()
+                        assert (kh, kw) not in where          # every deconv tap lands in exactly one place
+                        where[(kh, kw)] = (rh, rw, th, tw)
+    assert len(where) == k * k
+    y = torch.nn.functional.conv2d(x, w3.reshape(4 * Cout, Cin, 3, 3), padding=1)          # [B, (rh,rw,co), H, W]
+    out = y.reshape(2, 2, 2, Cout, H, W).permute(0, 3, 4, 1, 5, 2).reshape(2, Cout, 2 * H, 2 * W)
+    assert ref.shape == out.shape and (ref - out).abs().max() < 1e-12
+    # the kernel's closed form for the way back: rh = (kh - pad) & 1, th = (rh + pad - kh) / 2 + 1
+    for (kh, kw), (rh, rw, th, tw) in where.items():
+        assert rh == (kh - pad) & 1 and rw == (kw - pad) & 1
+        assert th == (rh + pad - kh) // 2 + 1 and tw == (rw + pad - kw) // 2 + 1
+        assert (rh + pad - kh) % 2 == 0 and (rw + pad - kw) % 2 == 0
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # decode tail (tests/golden/decode2.npz: the reference's get_final_preds / accuracy / oks_nms / generate_target)
 # --------------------------------------------------------------------------------------------------------------------
