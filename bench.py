@@ -58,6 +58,13 @@ CONFIGS = {
         family="hourglass", student=(128, 4), teacher=None, batch=128, H=256, W=256, J=16, lr=0.0,
         flop_per_image=15.629e9, kind="infer",
         roof=dict(cin=64, cout=64, k=3, h=64, w=64)),
+    # --- beyond BASELINE.json: the third registered model family, as experiments/mpii/resnet/res50_256x256_*
+    "res50_mse": dict(
+        workload="pose_resnet-50 (3 x 256-filter 4x4 deconv head) train, MSE only (function.train), 256x256, batch 32/GPU",
+        family="resnet", student=50, teacher=None, batch=32, H=256, W=256, J=16, lr=1e-3,
+        flop_per_image=3 * 2 * 7234125824.0, kind="train",
+        # 3x3 128->128 @32x32 (layer2 conv2, 4 launches) stands for the body's 3x3 convolutions
+        roof=dict(cin=128, cout=128, k=3, h=32, w=32)),
     # --- diagnostics (not BASELINE configs): the two halves of hg_fpd on their own
     "diag_student": dict(
         workload="[diagnostic] hourglass s4 f128 train, MSE only, 256x256, batch 32 (the student half of hg_fpd)",
@@ -85,6 +92,13 @@ class _Cfg(dict):
 
 def _wrap(d):
     return _Cfg({k: _wrap(v) for k, v in d.items()}) if isinstance(d, dict) else d
+
+
+def resnet_cfg(num_layers, j=16):
+    """experiments/mpii/resnet/res*_256x256_d256x3_adam_lr1e-3.yaml, MODEL.EXTRA."""
+    return NS(MODEL=NS(NUM_JOINTS=j, INIT_WEIGHTS=False, PRETRAINED='', EXTRA=NS(
+        NUM_LAYERS=num_layers, DECONV_WITH_BIAS=False, NUM_DECONV_LAYERS=3, NUM_DECONV_FILTERS=[256, 256, 256],
+        NUM_DECONV_KERNELS=[4, 4, 4], FINAL_CONV_KERNEL=1)))
 
 
 def hrnet_cfg(w, j=17):
@@ -206,7 +220,7 @@ def measured_peaks():
 # from the committed sweep profiles/r2_cpu_thread_sweep.txt (tools/cpu_thread_sweep.py): more threads or larger batches
 # are SLOWER per image there (hg_fpd: 6.7 img/s at B=4 / 16 threads, 3.0 at B=8, 1.6 at B=32; 1.1 with 64 threads), so the
 # CPU legs run the sample size and thread count the reference is fastest with. FPD_CPU_THREADS / --batch override.
-CPU_BEST = {"hg_fpd": (4, 16), "hg_mse_s1": (2, 8), "hrnet_fpd": (8, 16), "hg_infer": (8, 16)}
+CPU_BEST = {"hg_fpd": (4, 16), "hg_mse_s1": (2, 8), "hrnet_fpd": (8, 16), "hg_infer": (8, 16), "res50_mse": (8, 16)}
 
 
 def cpu_threads(name=None):
@@ -232,6 +246,8 @@ class CpuReference:
         if self.kind == "reference":
             if c["family"] == "hourglass":
                 mk = lambda fs: R.hourglass().get_pose_net(R.hg_cfg(fs[0], fs[1], c["J"]), True)   # noqa: E731
+            elif c["family"] == "resnet":
+                mk = lambda n: R.pose_resnet().get_pose_net(R.resnet_cfg(n, c["J"]), False)        # noqa: E731
             else:
                 mk = lambda w: R.pose_hrnet().get_pose_net(R.hrnet_cfg(w), False)                  # noqa: E731
             self.student = mk(c["student"])
@@ -428,6 +444,10 @@ def build_models(name, dev):
         from fpd_b200.lib.models import hourglass as H
         student = H.get_pose_net(cfg(c["student"][0], c["student"][1], c["J"]), True).to(dev)
         teacher = H.get_pose_net(cfg(c["teacher"][0], c["teacher"][1], c["J"]), False).to(dev) if c["teacher"] else None
+    elif c["family"] == "resnet":
+        from fpd_b200.lib.models import pose_resnet as H
+        student = H.get_pose_net(resnet_cfg(c["student"], c["J"]), False).to(dev)
+        teacher = H.get_pose_net(resnet_cfg(c["teacher"], c["J"]), False).to(dev) if c["teacher"] else None
     else:
         from fpd_b200.lib.models import pose_hrnet as H
         student = H.get_pose_net(hrnet_cfg(c["student"], c["J"]), False).to(dev)

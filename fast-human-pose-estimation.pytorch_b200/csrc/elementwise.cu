@@ -49,14 +49,16 @@ bn_stats_partial_kernel(const float* __restrict__ x, int64_t P, int C, int L, in
                         double* __restrict__ part /*[nblocks][C][2]*/) {
   extern __shared__ double sm[];  // [R][C][2] (mean, M2) + counts [R]
   const int tid = threadIdx.x;
-  const int cx = tid % L;
-  const int ry = tid / L;
+  // more than 4 x 256 channels (pose_resnet's 2048-channel layer4): the block walks the channel lanes in segments of 256
+  const int Lc = L < kRedThreads ? L : kRedThreads;
+  const int ry = tid / Lc;
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
   int64_t row1 = row0 + rows_per_block;
   if (row1 > P) row1 = P;
-  float piv[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-  int n = 0;
-  if (ry < R) {
+  if (ry < R)
+  for (int cx = tid % Lc; cx < L; cx += Lc) {
+    float piv[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    int n = 0;
     for (int64_t r = row0 + ry; r < row1; r += R) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C) + cx);
       const float e[4] = {v.x, v.y, v.z, v.w};
@@ -327,13 +329,14 @@ channel_reduce_partial_kernel(F f, int64_t P, int C, int L, int R, int64_t rows_
                               float* __restrict__ amax_scale /*[2] or null*/ = nullptr) {
   extern __shared__ double sm[];  // [R][NV][C]
   const int tid = threadIdx.x;
-  const int cx = tid % L;
-  const int ry = tid / L;
+  const int Lc = L < kRedThreads ? L : kRedThreads;   // > 1024 channels: channel lanes in segments of 256 (see bn_stats)
+  const int ry = tid / Lc;
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
   int64_t row1 = row0 + rows_per_block;
   if (row1 > P) row1 = P;
   float tmax = 0.f;   // max |v[0]| seen by this thread (used by the fused form's amax output)
-  if (ry < R) {
+  if (ry < R)
+  for (int cx = tid % Lc; cx < L; cx += Lc) {
     double acc[NV][4];
 #pragma unroll
     for (int k = 0; k < NV; ++k)
@@ -1070,7 +1073,7 @@ size_t bn_stats_workspace_bytes(int64_t P, int C) {
 
 int bn_stats(const float* x, int64_t P, int C, float* mean, float* var_biased, void* workspace, size_t ws_bytes,
              cudaStream_t stream) {
-  FPD_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "bn_stats: C=%d must be a multiple of 4 in [4,1024]", C);
+  FPD_REQUIRE(C % 4 == 0 && C >= 4 && C <= 4096, "bn_stats: C=%d must be a multiple of 4 in [4,4096]", C);
   FPD_REQUIRE(P > 0, "bn_stats: empty tensor");
   RedGeom g = red_geom(P, C);
   FPD_REQUIRE(ws_bytes >= (size_t)g.nblocks * C * 2 * sizeof(double), "bn_stats: workspace too small");
@@ -1255,7 +1258,7 @@ static int run_channel_reduce_fused(F f, int64_t P, int C, float scale, float* o
   // kernel, but measured ~2x slower on B200 (one wave of blocks starves the main pass of memory parallelism, many blocks
   // make the one-CTA tail long), so the counter is accepted for ABI stability and ignored.
   (void)counter;
-  FPD_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "channel reduce: C=%d must be a multiple of 4 in [4,1024]", C);
+  FPD_REQUIRE(C % 4 == 0 && C >= 4 && C <= 4096, "channel reduce: C=%d must be a multiple of 4 in [4,4096]", C);
   RedGeom g = red_geom(P, C);
   FPD_REQUIRE(ws_bytes >= (size_t)g.nblocks * NV * C * sizeof(double) + (size_t)g.nblocks * sizeof(float),
               "channel reduce: workspace too small");
@@ -1279,7 +1282,7 @@ static int run_channel_reduce_fused(F f, int64_t P, int C, float scale, float* o
 template <int NV, class F>
 static int run_channel_reduce(F f, int64_t P, int C, float scale, float* out, void* workspace, size_t ws_bytes,
                               cudaStream_t stream) {
-  FPD_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "channel reduce: C=%d must be a multiple of 4 in [4,1024]", C);
+  FPD_REQUIRE(C % 4 == 0 && C >= 4 && C <= 4096, "channel reduce: C=%d must be a multiple of 4 in [4,4096]", C);
   RedGeom g = red_geom(P, C);
   FPD_REQUIRE(ws_bytes >= (size_t)g.nblocks * NV * C * sizeof(double), "channel reduce: workspace too small");
   const size_t smem = (size_t)g.R * NV * C * sizeof(double);
@@ -1344,7 +1347,7 @@ int bn_stats_fused(const float* x, int64_t P, int C, const float* gamma, const f
                    float* rmean, float* rvar, float* mean, float* var, float* scale, float* shift, float* invstd,
                    void* workspace, size_t ws_bytes, unsigned int* counter, cudaStream_t stream) {
   (void)counter;   // see run_channel_reduce_fused: two launches (partial + final/finalize) instead of three
-  FPD_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "bn_stats_fused: C=%d must be a multiple of 4 in [4,1024]", C);
+  FPD_REQUIRE(C % 4 == 0 && C >= 4 && C <= 4096, "bn_stats_fused: C=%d must be a multiple of 4 in [4,4096]", C);
   FPD_REQUIRE(P > 0 && mean && var && scale && shift, "bn_stats_fused: bad argument");
   FPD_REQUIRE((rmean == nullptr) == (rvar == nullptr), "bn_stats_fused: running stats come in pairs");
   RedGeom g = red_geom(P, C);

@@ -77,6 +77,35 @@ SCRIPT = textwrap.dedent('''
                                                   NUM_JOINTS=16))
     net = models.hourglass.get_pose_net(c, is_train=True)
     assert "hg.0.hg.3.0.0.conv2.weight" in net.state_dict()
+    # checkpoint formats (SURVEY 8 f4): the reference's OWN save_checkpoint / load_checkpoint (utils/utils.py:74-86,
+    # 204-251: plain state_dict, DataParallel 'module.'-prefixed, and the {'state_dict': ...} training checkpoint, plus the
+    # filter_keys partial load the FPD student uses) round-trip through the drop-in modules of all three families
+    import os, tempfile, torch
+    from utils.utils import load_checkpoint
+    rcfg = T.SimpleNamespace(MODEL=T.SimpleNamespace(NUM_JOINTS=16, INIT_WEIGHTS=False, PRETRAINED='', EXTRA=T.SimpleNamespace(
+        NUM_LAYERS=18, DECONV_WITH_BIAS=False, NUM_DECONV_LAYERS=2, NUM_DECONV_FILTERS=[32, 32], NUM_DECONV_KERNELS=[4, 4],
+        FINAL_CONV_KERNEL=1)))
+    with tempfile.TemporaryDirectory() as d:
+        for mk in (lambda: models.hourglass.get_pose_net(c, is_train=False),
+                   lambda: models.pose_resnet.get_pose_net(rcfg, is_train=False)):
+            src, dst = mk(), mk()
+            for p_ in src.parameters():
+                p_.data.normal_()
+            sd = src.state_dict()
+            opt = get_optimizer(T.SimpleNamespace(TRAIN=T.SimpleNamespace(OPTIMIZER='adam', LR=1e-3)), src)
+            save_checkpoint({'epoch': 3, 'model': 'x', 'state_dict': sd, 'best_state_dict': sd, 'perf': 0.5,
+                             'optimizer': opt.state_dict()}, True, d)
+            assert os.path.exists(os.path.join(d, 'checkpoint.pth')) and os.path.exists(os.path.join(d, 'model_best.pth'))
+            load_checkpoint(os.path.join(d, 'checkpoint.pth'), dst, model_info='ckpt')            # training checkpoint
+            assert all(torch.equal(sd[k], v) for k, v in dst.state_dict().items())
+            dst = mk()
+            torch.save({'module.' + k: v for k, v in sd.items()}, os.path.join(d, 'dp.pth'))      # DataParallel keys
+            load_checkpoint(os.path.join(d, 'dp.pth'), dst, model_info='dp')
+            assert all(torch.equal(sd[k], v) for k, v in dst.state_dict().items())
+            dst = mk()
+            load_checkpoint(os.path.join(d, 'model_best.pth'), dst, strict=False, filter_keys='bn1', model_info='part')
+            assert all(torch.equal(sd[k], v) for k, v in dst.state_dict().items() if 'bn1' not in k)
+            assert not torch.equal(sd['bn1.weight'], dst.state_dict()['bn1.weight'])
     # shadowing guard: our lib/ on sys.path is refused loudly
     dropin.uninstall()
     for k in [k for k in sys.modules if k.split(".")[0] in ("models", "core", "nms", "utils", "dataset")]:
