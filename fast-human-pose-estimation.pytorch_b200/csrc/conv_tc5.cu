@@ -50,8 +50,8 @@ constexpr int kEpiBytes = 4 * 32 * 128;   // epilogue staging: one [32 rows x 12
 // (TMEM read-out, residual loads, global stores) is what bounds the kernel (r1 stall counters), so the warp budget is
 // re-cut there: 4 transform warps (each thread does both 32-channel halves of its row, waiting for the first half's
 // tcgen05.st before it reuses the registers) and 8 epilogue warps (warps 2-5 take the even 32-column groups of a tile,
-// warps 10-13 the odd ones; a TMEM lane quarter may be read by any warp with the same warp % 4). FPD_CONV_EPI8=0
-// restores the 8 + 4 split of the 3x3 path.
+// warps 10-13 the odd ones; a TMEM lane quarter may be read by any warp with the same warp % 4) -- where the epilogue is
+// the heavier side; shapes whose input is the wide side keep the 8 + 4 split of the 3x3 path (plan() decides per launch).
 constexpr int kEpiBytes8 = 8 * 32 * 128;
 
 struct ConvHParams {
@@ -800,9 +800,17 @@ int pow2_floor_div(int x, int cap) {
 int align1024(int x) { return (x + 1023) / 1024 * 1024; }
 
 // Fills the geometry / ring sizes; returns false if the shape does not fit.
-bool plan(ConvHParams& p, int B, int H, int W, int Cin, int Cout, int ksize, int f16, int passes, int stats = 0) {
-  static const bool epi8_ok = [] { const char* e = getenv("FPD_CONV_EPI8"); return !(e && e[0] == '0'); }();
-  p.epi8 = (ksize == 1 && epi8_ok) ? 1 : 0;
+// epi_inputs: bit 0 = the epilogue adds a residual, bit 1 = it applies a ReLU mask (each one more tensor it has to load).
+bool plan(ConvHParams& p, int B, int H, int W, int Cin, int Cout, int ksize, int f16, int passes, int stats = 0,
+          int epi_inputs = 0) {
+  // Warp split of the 1x1 path, per shape (profiles/r2_conv1x1_split.txt, both splits timed on every 1x1 shape of the two
+  // hourglasses): the transform's work per tile grows with Cin, the epilogue's with Cout and with every extra tensor it
+  // reads. 4 transform + 8 epilogue warps win where (1 + 1.5 residual + mask) x Cout > Cin (128->256 + residual: 108 vs
+  // 135 us; 64->128: 31 vs 38), 8 + 4 where the input is the wide side (256->128: 56 vs 70 us; 256->256: 95 vs 123;
+  // 256->16: 44 vs 60). FPD_CONV_EPI8 = 0 / 1 forces one split everywhere.
+  static const int epi8_mode = [] { const char* e = getenv("FPD_CONV_EPI8"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+  const bool epi8_pays = Cout * (2 + 3 * (epi_inputs & 1) + 2 * ((epi_inputs >> 1) & 1)) > 2 * Cin;
+  p.epi8 = (ksize == 1 && (epi8_mode == 1 || (epi8_mode < 0 && epi8_pays))) ? 1 : 0;
   p.epi_bytes = p.epi8 ? kEpiBytes8 : kEpiBytes;
   p.stat_bytes = 0;
   if (stats) {
@@ -910,7 +918,8 @@ int conv_tc_h_launch(const float* x, const float* pre_mean, const float* pre_sca
   FPD_REQUIRE((pre_scale == nullptr) == (pre_shift == nullptr), "conv_tc_h: pre_scale/pre_shift come in pairs");
   FPD_REQUIRE(pre_scale != nullptr || pre_mean == nullptr, "conv_tc_h: pre_mean needs pre_scale/pre_shift");
   ConvHParams p{};
-  FPD_REQUIRE(plan(p, B, H, W, Cin, Cout, ksize, f16, w_lo ? 3 : 1, stat_part ? 1 : 0),
+  FPD_REQUIRE(plan(p, B, H, W, Cin, Cout, ksize, f16, w_lo ? 3 : 1, stat_part ? 1 : 0,
+                   (residual ? 1 : 0) | (relu_mask ? 2 : 0)),
               "conv_tc_h: unsupported shape Cin=%d Cout=%d k=%d H=%d W=%d f16=%d stats=%d", Cin, Cout, ksize, H, W, f16,
               stat_part ? 1 : 0);
   p.stat_part = stat_part;
