@@ -44,6 +44,7 @@ inline RedGeom red_geom(int64_t P, int C, int max_blocks) {
 // -------------------------------------------------------------------------------------------------
 // BN statistics: per block -> (n, mean, M2) per channel, merged with Chan's parallel formula in fp64.
 // -------------------------------------------------------------------------------------------------
+template <bool kWide>   // kWide: more than 1024 channels (the common narrow form keeps its single-trip code)
 __global__ void __launch_bounds__(kRedThreads)
 bn_stats_partial_kernel(const float* __restrict__ x, int64_t P, int C, int L, int R, int64_t rows_per_block,
                         double* __restrict__ part /*[nblocks][C][2]*/) {
@@ -55,8 +56,9 @@ bn_stats_partial_kernel(const float* __restrict__ x, int64_t P, int C, int L, in
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
   int64_t row1 = row0 + rows_per_block;
   if (row1 > P) row1 = P;
+  const int cx0 = tid % Lc;
   if (ry < R)
-  for (int cx = tid % Lc; cx < L; cx += Lc) {
+  for (int cx = cx0; kWide ? cx < L : cx == cx0; cx += kRedThreads) {
     float piv[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     int n = 0;
     for (int64_t r = row0 + ry; r < row1; r += R) {
@@ -321,7 +323,7 @@ __device__ __forceinline__ void write_amax_scale(float m, float* amax_scale) {
   amax_scale[1] = 1.f / S;
 }
 
-template <int NV, class F>
+template <int NV, class F, bool kWide = false>
 __global__ void __launch_bounds__(kRedThreads)
 channel_reduce_partial_kernel(F f, int64_t P, int C, int L, int R, int64_t rows_per_block,
                               double* __restrict__ part /*[nblocks][NV][C]*/, unsigned int* counter = nullptr,
@@ -335,8 +337,9 @@ channel_reduce_partial_kernel(F f, int64_t P, int C, int L, int R, int64_t rows_
   int64_t row1 = row0 + rows_per_block;
   if (row1 > P) row1 = P;
   float tmax = 0.f;   // max |v[0]| seen by this thread (used by the fused form's amax output)
+  const int cx0 = tid % Lc;
   if (ry < R)
-  for (int cx = tid % Lc; cx < L; cx += Lc) {
+  for (int cx = cx0; kWide ? cx < L : cx == cx0; cx += kRedThreads) {
     double acc[NV][4];
 #pragma unroll
     for (int k = 0; k < NV; ++k)
@@ -1080,12 +1083,18 @@ int bn_stats(const float* x, int64_t P, int C, float* mean, float* var_biased, v
   const size_t smem = ((size_t)g.R * C * 2 + g.R) * sizeof(double);
   static bool attr = false;
   if (!attr) {
-    FPD_CUDA_CHECK(cudaFuncSetAttribute(bn_stats_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(bn_stats_partial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        160 * 1024));
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(bn_stats_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         160 * 1024));
     attr = true;
   }
-  bn_stats_partial_kernel<<<g.nblocks, kRedThreads, smem, stream>>>(x, P, C, g.L, g.R, g.rows_per_block,
-                                                                    (double*)workspace);
+  if (C > 4 * kRedThreads)
+    bn_stats_partial_kernel<true><<<g.nblocks, kRedThreads, smem, stream>>>(x, P, C, g.L, g.R, g.rows_per_block,
+                                                                            (double*)workspace);
+  else
+    bn_stats_partial_kernel<false><<<g.nblocks, kRedThreads, smem, stream>>>(x, P, C, g.L, g.R, g.rows_per_block,
+                                                                             (double*)workspace);
   FPD_LAUNCH_CHECK();
   bn_stats_final_kernel<<<(C * 32 + 127) / 128, 128, 0, stream>>>((const double*)workspace, g.nblocks,
                                                              g.rows_per_block, P, C, mean, var_biased);
@@ -1265,12 +1274,18 @@ static int run_channel_reduce_fused(F f, int64_t P, int C, float scale, float* o
   const size_t smem = (size_t)g.R * NV * C * sizeof(double);
   static bool attr = false;
   if (!attr) {
-    FPD_CUDA_CHECK(cudaFuncSetAttribute(channel_reduce_partial_kernel<NV, F>,
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(channel_reduce_partial_kernel<NV, F, false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(channel_reduce_partial_kernel<NV, F, true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr = true;
   }
-  channel_reduce_partial_kernel<NV, F><<<g.nblocks, kRedThreads, smem, stream>>>(
-      f, P, C, g.L, g.R, g.rows_per_block, (double*)workspace, nullptr, scale, out, amax_scale);
+  if (C > 4 * kRedThreads)
+    channel_reduce_partial_kernel<NV, F, true><<<g.nblocks, kRedThreads, smem, stream>>>(
+        f, P, C, g.L, g.R, g.rows_per_block, (double*)workspace, nullptr, scale, out, amax_scale);
+  else
+    channel_reduce_partial_kernel<NV, F, false><<<g.nblocks, kRedThreads, smem, stream>>>(
+        f, P, C, g.L, g.R, g.rows_per_block, (double*)workspace, nullptr, scale, out, amax_scale);
   FPD_LAUNCH_CHECK();
   const int warps = NV * C + (amax_scale ? 1 : 0);
   channel_reduce_final_kernel<<<(warps * 32 + 127) / 128, 128, 0, stream>>>((const double*)workspace, g.nblocks, NV * C,
@@ -1288,13 +1303,20 @@ static int run_channel_reduce(F f, int64_t P, int C, float scale, float* out, vo
   const size_t smem = (size_t)g.R * NV * C * sizeof(double);
   static bool attr = false;
   if (!attr) {
-    FPD_CUDA_CHECK(cudaFuncSetAttribute(channel_reduce_partial_kernel<NV, F>,
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(channel_reduce_partial_kernel<NV, F, false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(channel_reduce_partial_kernel<NV, F, true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr = true;
   }
-  channel_reduce_partial_kernel<NV, F><<<g.nblocks, kRedThreads, smem, stream>>>(f, P, C, g.L, g.R,
-                                                                                  g.rows_per_block,
-                                                                                  (double*)workspace);
+  if (C > 4 * kRedThreads)
+    channel_reduce_partial_kernel<NV, F, true><<<g.nblocks, kRedThreads, smem, stream>>>(f, P, C, g.L, g.R,
+                                                                                          g.rows_per_block,
+                                                                                          (double*)workspace);
+  else
+    channel_reduce_partial_kernel<NV, F, false><<<g.nblocks, kRedThreads, smem, stream>>>(f, P, C, g.L, g.R,
+                                                                                           g.rows_per_block,
+                                                                                           (double*)workspace);
   FPD_LAUNCH_CHECK();
   channel_reduce_final_kernel<<<(NV * C * 32 + 127) / 128, 128, 0, stream>>>((const double*)workspace, g.nblocks, NV * C,
                                                                         scale, out);
@@ -1355,12 +1377,18 @@ int bn_stats_fused(const float* x, int64_t P, int C, const float* gamma, const f
   const size_t smem = ((size_t)g.R * C * 2 + g.R) * sizeof(double);
   static bool attr = false;
   if (!attr) {
-    FPD_CUDA_CHECK(cudaFuncSetAttribute(bn_stats_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(bn_stats_partial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        160 * 1024));
+    FPD_CUDA_CHECK(cudaFuncSetAttribute(bn_stats_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         160 * 1024));
     attr = true;
   }
-  bn_stats_partial_kernel<<<g.nblocks, kRedThreads, smem, stream>>>(x, P, C, g.L, g.R, g.rows_per_block,
-                                                                    (double*)workspace);
+  if (C > 4 * kRedThreads)
+    bn_stats_partial_kernel<true><<<g.nblocks, kRedThreads, smem, stream>>>(x, P, C, g.L, g.R, g.rows_per_block,
+                                                                            (double*)workspace);
+  else
+    bn_stats_partial_kernel<false><<<g.nblocks, kRedThreads, smem, stream>>>(x, P, C, g.L, g.R, g.rows_per_block,
+                                                                             (double*)workspace);
   FPD_LAUNCH_CHECK();
   BnFinalize fz{gamma, beta, eps, momentum, mean, var, scale, shift, invstd, rmean, rvar};
   bn_stats_final_finalize_kernel<<<(C + 3) / 4, 256, 0, stream>>>((const double*)workspace, g.nblocks,
