@@ -75,6 +75,24 @@ def test_kernel_shape_planners_on_cpu():
     assert lib.fpd_conv2d_tc_h_supported(6, 64, 1, 64, 64, 1) == 0             # fp16 rows need Cin % 8 == 0 ...
     assert lib.fpd_conv2d_tc_h_supported(12, 64, 1, 64, 64, 0) == 1            # ... tf32 rows Cin % 4 == 0
     assert lib.fpd_conv2d_tc_h_supported(64, 24, 1, 64, 64, 0) == 0            # Cout % 16
+    # pose_resnet-50/101/152 (layer2..4, the deconv head as 3x3 convs to 4 x 256 channels, and their data gradients) at
+    # 256x256 and 256x192 inputs: up to 2048 channels in, 2048 out (BN-parameter shared memory is sized per launch)
+    for (h, w) in ((8, 8), (8, 6), (16, 16), (16, 12), (32, 24)):
+        for (cin, cout, k) in ((2048, 512, 1), (512, 2048, 1), (1024, 2048, 1), (512, 512, 3), (2048, 1024, 3),
+                               (1024, 2048, 3), (1024, 256, 1), (256, 1024, 3)):
+            for f16 in (0, 1):
+                assert lib.fpd_conv2d_tc_h_supported(cin, cout, k, h, w, f16) == 1, (cin, cout, k, h, w, f16)
+    assert lib.fpd_conv2d_tc_h_supported(4096, 512, 1, 8, 8, 1) == 0
+    assert lib.fpd_conv2d_tc_h_supported(512, 4096, 1, 8, 8, 1) == 0
+    # ... their weight gradients go per (Cin, Cout) chunk through the tensor-core kernels
+    from fpd_b200 import ops
+    assert ops.wgrad_channel_chunks(64, 64, 3) == (64, 64)                     # one launch
+    assert ops.wgrad_channel_chunks(256, 256, 3) == (128, 256)                 # HRNet / ResNet layer3: Cin in two halves
+    assert ops.wgrad_channel_chunks(512, 512, 3) == (128, 256)
+    assert ops.wgrad_channel_chunks(2048, 1024, 3) == (128, 256)               # first deconv of ResNet-50 as a 3x3 conv
+    assert ops.wgrad_channel_chunks(2048, 512, 1) == (256, 512)                # 1x1: any Cout, Cin <= 256 per launch
+    assert ops.wgrad_channel_chunks(256, 1024, 1) == (256, 1024)
+    assert ops.wgrad_channel_chunks(32, 17, 3) is None                         # 17-joint head: CUDA-core path
     # halo weight-gradient kernel: 3x3, Cin in {64, 128}, W % 8 == 0, at least two pipeline stages must fit
     for hw in (64, 32, 16, 8):
         assert lib.fpd_conv2d_wgrad_tc3_supported(hw, hw, 64, 64, 3) == 1
