@@ -263,6 +263,20 @@ def test_resnet_dropin_matches_reference_layout_and_refuses_cpu():
             a = R.get_pose_net(_resnet_cfg(tag), is_train=False).state_dict()
             b = M.get_pose_net(_resnet_cfg(tag), is_train=False).state_dict()
             assert list(a.keys()) == list(b.keys()) and all(a[k].shape == b[k].shape for k in a)
+        for depth in (34, 101, 152):          # the shipped d256x3 head on the remaining depths of resnet_spec
+            cfg = _resnet_cfg("r50")
+            cfg.MODEL.EXTRA.NUM_LAYERS = depth
+            cfg.MODEL.EXTRA.NUM_DECONV_FILTERS = [256, 256, 256]
+            a = R.get_pose_net(cfg, is_train=False).state_dict()
+            b = M.get_pose_net(cfg, is_train=False).state_dict()
+            assert list(a.keys()) == list(b.keys()) and all(a[k].shape == b[k].shape for k in a), depth
+        # init_weights without a checkpoint (pose_resnet.py:229-247): N(0, 0.001) convs / deconvs, unit BatchNorm
+        cfg = _resnet_cfg("r18")
+        cfg.MODEL.INIT_WEIGHTS = True
+        net = M.get_pose_net(cfg, is_train=True)
+        assert 5e-4 < net.layer2[0].conv1.weight.std().item() < 2e-3
+        assert 5e-4 < net.deconv_layers[0].weight.std().item() < 2e-3 and float(net.deconv_layers[0].bias.detach().abs().max()) == 0.0
+        assert torch.equal(net.deconv_layers[1].weight, torch.ones_like(net.deconv_layers[1].weight))
 
 
 @pytest.mark.parametrize("k,pad,outpad", [(4, 1, 0), (3, 1, 1), (2, 0, 0)])
